@@ -1,0 +1,323 @@
+// pi3b_gemm: C[M,N] = epilogue(A[M,K] * W[N,K]^T) on tcgen05 tensor cores (sm_100a).
+//
+// Replaces every nn.Linear on the pi3 chunk forward (reference: pi3/models/layers/attention.py:256-258,
+// pi3/models/dinov2/layers/mlp.py:29-31, pi3/models/layers/transformer_head.py:24,46,68,
+// pi3/models/layers/camera_head.py:21-23,40-46) and the patch-embed conv-as-GEMM
+// (pi3/models/dinov2/layers/patch_embed.py:65,75).
+//
+// Design: persistent CTAs (one per SM), tile 128 x BLOCK_N x 128 B of K, TMA (SWIZZLE_128B) into a
+// multi-stage smem ring, one elected thread issues tcgen05.mma (cta_group::1, M=128, N=BLOCK_N) into a
+// double-buffered TMEM accumulator, eight epilogue warps drain TMEM with tcgen05.ld (one output row per
+// thread) and apply the fused epilogue  out = [resid +] gamma * act(acc + bias)  straight to HBM, so
+// the epilogue of tile i overlaps the main loop of tile i+1.  Operands: bf16 (kind::f16) or fp32 read
+// as TF32 (kind::tf32, used for the fp32 heads the reference runs with autocast disabled).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace pi3b {
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;   // [N] or null
+  const float* gamma;  // [N] or null (LayerScale)
+  const float* resid;  // fp32 [M, ld_resid] or null (may alias out)
+  void* out;           // bf16 or fp32 [M, ldo]
+  int ldo, ld_resid;
+  int out_f32;  // 1: fp32 output, 0: bf16 output
+  int act;      // 0 none, 1 GELU(erf), 2 ReLU
+};
+
+constexpr int kBlockM = 128;
+constexpr int kNumEpiWarps = 8;
+constexpr int kGemmThreads = 64 + kNumEpiWarps * 32;
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = kBlockM * 128;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024: manual alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BLOCK_N, int STAGES, bool TF32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using S = GemmSmem<BLOCK_N, STAGES>;
+  constexpr int ELEM = TF32 ? 4 : 2;
+  constexpr int BLOCK_K = 128 / ELEM;  // elements per 128-byte smem row
+  constexpr int UMMA_K = 32 / ELEM;    // 16 (bf16) / 8 (tf32): 32 bytes of K per instruction
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          // activations stream through once; the (small) weight panel is reused by every m block
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * kBlockM, kEvictNormal);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, kEvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TF32 ? 2u : 1u, kBlockM, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            if (TF32)
+              umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            else
+              umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> fused epilogue -> HBM =====
+    const int ew = warp - 2;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
+    const int half = ew >> 2;                // which half of the BLOCK_N columns
+    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int m = m_blk * kBlockM + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+        const int col_in_tile = half * COLS_PER_WARP + c * 32;
+        const int n0 = n_blk * BLOCK_N + col_in_tile;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N + col_in_tile, r);
+        tmem_ld_wait();
+        const int nvalid = min(32, p.N - n0);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (nvalid == 32) {
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.gamma) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j));
+              v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+            }
+          }
+          if (row_ok) {
+            if (p.resid) {
+              const float4* rp = reinterpret_cast<const float4*>(p.resid + size_t(m) * p.ld_resid + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 x = rp[j];
+                v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+              }
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(m) * p.ldo + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + size_t(m) * p.ldo + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            }
+          }
+        } else if (row_ok) {
+          // ragged N tail (N = 588 / 196 / 9 / 3 heads): scalar path
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+              float x = v[j];
+              if (p.bias) x += __ldg(p.bias + n0 + j);
+              if (p.act == 1) x = gelu_erf(x);
+              else if (p.act == 2) x = fmaxf(x, 0.f);
+              if (p.gamma) x *= __ldg(p.gamma + n0 + j);
+              if (p.resid) x += p.resid[size_t(m) * p.ld_resid + n0 + j];
+              if (p.out_f32) static_cast<float*>(p.out)[size_t(m) * p.ldo + n0 + j] = x;
+              else static_cast<__nv_bfloat16*>(p.out)[size_t(m) * p.ldo + n0 + j] = __float2bfloat16(x);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, int STAGES, bool TF32>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
+                       cudaStream_t stream) {
+  using S = GemmSmem<BLOCK_N, STAGES>;
+  auto kern = gemm_kernel<BLOCK_N, STAGES, TF32>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+      return check_launch("gemm: cudaFuncSetAttribute");
+    configured = true;
+  }
+  const int num_tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  kern<<<grid, kGemmThreads, S::TOTAL, stream>>>(tmA, tmB, p);
+  return check_launch("gemm launch");
+}
+
+static int cached_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace pi3b
+
+using namespace pi3b;
+
+// See include/pi3b200.h for the contract.
+extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda, const void* W, int64_t ldw, int M,
+                         int N, int K, const float* bias, const float* gamma, const float* resid, int64_t ld_resid,
+                         void* out, int64_t ldo, int out_f32, int act) {
+  PI3B_REQUIRE(A && W && out, "pi3b_gemm: null pointer");
+  PI3B_REQUIRE(M > 0 && N > 0 && K > 0, "pi3b_gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  PI3B_REQUIRE(in_dtype == 0 || in_dtype == 1, "pi3b_gemm: in_dtype must be 0 (bf16) or 1 (fp32->tf32)");
+  PI3B_REQUIRE(act >= 0 && act <= 2, "pi3b_gemm: act must be 0/1/2");
+  const int esz = in_dtype == 0 ? 2 : 4;
+  PI3B_REQUIRE((lda * esz) % 16 == 0 && (ldw * esz) % 16 == 0, "pi3b_gemm: lda/ldw must give 16-byte row pitch");
+  PI3B_REQUIRE(lda >= K && ldw >= K, "pi3b_gemm: lda/ldw < K");
+  PI3B_REQUIRE(ldo % (out_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "pi3b_gemm: output must be 16-byte aligned with ldo %% %d == 0", out_f32 ? 4 : 8);
+  PI3B_REQUIRE(!resid || (ld_resid % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0),
+               "pi3b_gemm: resid must be 16-byte aligned with ld %% 4 == 0");
+  PI3B_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "pi3b_gemm: bias must be 16-byte aligned");
+  PI3B_REQUIRE(!gamma || (reinterpret_cast<uintptr_t>(gamma) & 15) == 0, "pi3b_gemm: gamma must be 16-byte aligned");
+
+  const int num_sms = cached_num_sms();
+  const int block_k = 128 / esz;
+  // Use the wide tile when it still fills the machine; otherwise the narrow tile for more CTAs.
+  const int tiles256 = ((M + 127) / 128) * ((N + 255) / 256);
+  const bool wide = tiles256 >= num_sms && N > 128;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(&tmA, A, in_dtype, (uint64_t)M, (uint64_t)K, (uint64_t)lda * esz, 128, block_k);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, W, in_dtype, (uint64_t)N, (uint64_t)K, (uint64_t)ldw * esz, wide ? 256 : 128, block_k);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.gamma = gamma; p.resid = resid;
+  p.out = out; p.ldo = (int)ldo; p.ld_resid = (int)ld_resid;
+  p.out_f32 = out_f32; p.act = act;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in_dtype == 0) {
+    return wide ? launch_gemm<256, 4, false>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, false>(tmA, tmB, p, num_sms, st);
+  } else {
+    return wide ? launch_gemm<256, 4, true>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, true>(tmA, tmB, p, num_sms, st);
+  }
+}

@@ -1,0 +1,78 @@
+#include "host_common.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+namespace pi3b {
+
+static thread_local char g_err[512] = {0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return PI3B_ERR_CUDA;
+  }
+  return PI3B_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                 uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return PI3B_ERR_DRIVER;
+  }
+  const uint32_t esz = dtype == 0 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_bytes & 15) || box_cols * esz != 128 || box_rows > 256) {
+    set_error("make_tmap_2d: bad alignment/box (base=%p pitch=%llu box=%ux%u)", base,
+              (unsigned long long)pitch_bytes, box_rows, box_cols);
+    return PI3B_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu pitch=%llu box=%ux%u)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_bytes, box_rows, box_cols);
+    return PI3B_ERR_DRIVER;
+  }
+  return PI3B_OK;
+}
+
+}  // namespace pi3b
+
+extern "C" const char* pi3b_last_error() { return pi3b::g_err; }
+extern "C" int pi3b_version() { return 100; }
