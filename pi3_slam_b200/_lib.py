@@ -19,6 +19,8 @@ SIGNATURES = {
     "pi3b_last_error": (c_char_p, []),
     "pi3b_gemm": (c_int, [_P, c_int, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, _P,
                           c_int64, c_int, c_int]),
+    "pi3b_attn_fwd_hd64": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64,
+                                   c_int, c_int, c_int, c_float]),
 }
 
 

@@ -1,0 +1,353 @@
+// pi3b_attn_fwd_hd64: softmax(Q K^T / 8) V for head_dim 64, bf16 in / bf16 out, no mask.
+//
+// Replaces F.scaled_dot_product_attention on the pi3 chunk forward (reference:
+// pi3/models/layers/attention.py:102-104 and :336-338) for both regimes of Pi3.decode
+// (pi3/models/pi3.py:156-166): many frame-local sequences (S = T ~ 1k) and one chunk-global
+// sequence (S = N*T ~ 100k), which is ~75 % of the FLOPs of a chunk.
+//
+// Design (FA4-style, hand-written tcgen05):
+//   * one CTA = one (sequence, head, 256 query rows): two 128-row Q tiles ping-pong so that the
+//     tensor pipe works on one tile while the other tile's softmax runs on the SIMT/MUFU pipes;
+//   * warp 0 streams K/V tiles (128 rows x 64) with TMA into a 4-stage smem ring; warp 1 (one thread)
+//     issues S = Q K^T (M128 N128 K64, both operands K-major in smem) and O += P V (A = P from TMEM,
+//     B = V MN-major in smem); S, P and O all live in TMEM (2x128 + 2x64 + 2x64 = 512 columns);
+//   * warps 4-7 / 8-11 are the two softmax groups: one thread per query row (tcgen05.ld 32x32b), so
+//     row max / row sum need no shuffles; online softmax in the exp2 domain with lazy rescaling of O
+//     (only when the row max grows by more than 2^8), P written back to TMEM as packed bf16;
+//   * ragged tails: KV columns past the sequence end are masked to -inf, Q rows past it are not stored.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace pi3b {
+
+constexpr int kAttnThreads = 384;
+constexpr int kKvStages = 4;
+constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
+
+struct AttnSmem {
+  static constexpr int Q_OFF = 0;                                // 2 tiles
+  static constexpr int K_OFF = 2 * kTileBytes;                   // kKvStages tiles
+  static constexpr int V_OFF = K_OFF + kKvStages * kTileBytes;   // kKvStages tiles
+  static constexpr int BAR_OFF = V_OFF + kKvStages * kTileBytes;
+  // barriers: q_full, k_full[S], v_full[S], kv_empty[S], s_full[2], p_full[2], pv_done[2]
+  static constexpr int NUM_BARS = 1 + 3 * kKvStages + 6;
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
+};
+
+struct AttnParams {
+  int num_seqs, seq_len, num_heads;
+  int q_col0, k_col0, v_col0;  // element column of head 0 inside each operand's rows
+  __nv_bfloat16* out;
+  int ldo;
+  float scale_log2;  // softmax scale * log2(e)
+};
+
+// TMEM column map
+constexpr uint32_t kTmS = 0;     // S tile t at kTmS + t*128   (128 fp32 columns)
+constexpr uint32_t kTmO = 256;   // O tile t at kTmO + t*64    (64 fp32 columns)
+constexpr uint32_t kTmP = 384;   // P tile t at kTmP + t*64    (128 bf16 = 64 packed columns)
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::BAR_OFF);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = k_full + kKvStages;
+  uint64_t* kv_empty = v_full + kKvStages;
+  uint64_t* s_full = kv_empty + kKvStages;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* pv_done = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work item: query-pair fastest, then sequence, then head (neighbouring CTAs share one head's K/V in L2)
+  const int num_qpairs = (p.seq_len + 255) / 256;
+  int item = blockIdx.x;
+  const int qp = item % num_qpairs;
+  item /= num_qpairs;
+  const int seq = item % p.num_seqs;
+  const int head = item / p.num_seqs;
+  const int row_base = seq * p.seq_len;          // first row of this sequence in the operand matrices
+  const int q0 = qp * 256;                       // first query row (within the sequence) of this CTA
+  const int q_valid = min(256, p.seq_len - q0);  // valid query rows in this CTA
+  const int num_t = q_valid > 128 ? 2 : 1;       // second Q tile entirely past the end -> skip it
+  const int num_kv = (p.seq_len + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKvStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&pv_done[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // softmax threads hold a whole 128-wide score row in registers; the other warpgroup donates its budget
+  if (warp < 4) {
+   reg_dealloc<48>();
+   if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(q_full, num_t * kTileBytes);
+      for (int t = 0; t < num_t; ++t)
+        tma_load_2d(smem + AttnSmem::Q_OFF + t * kTileBytes, &tmQ, q_full, p.q_col0 + head * 64,
+                    row_base + q0 + t * 128, kEvictFirst);
+      for (int j = 0; j < num_kv; ++j) {
+        const int s = j % kKvStages;
+        const uint32_t ph = (j / kKvStages) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], kTileBytes);
+        tma_load_2d(smem + AttnSmem::K_OFF + s * kTileBytes, &tmK, &k_full[s], p.k_col0 + head * 64,
+                    row_base + j * 128, kEvictLast);
+        mbar_expect_tx(&v_full[s], kTileBytes);
+        tma_load_2d(smem + AttnSmem::V_OFF + s * kTileBytes, &tmV, &v_full[s], p.v_col0 + head * 64,
+                    row_base + j * 128, kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(1, 128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(1, 128, 64, 0, 1);  // B (=V) is MN-major
+      const uint32_t q_addr = smem_u32(smem + AttnSmem::Q_OFF);
+      const uint32_t k_addr = smem_u32(smem + AttnSmem::K_OFF);
+      const uint32_t v_addr = smem_u32(smem + AttnSmem::V_OFF);
+
+      auto issue_qk = [&](int t, int s) {
+        const uint32_t d = tmem_base + kTmS + t * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t adesc = make_smem_desc_sw128(q_addr + t * kTileBytes + k * 32, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(k_addr + s * kTileBytes + k * 32, 16, 1024);
+          umma_f16_ss(d, adesc, bdesc, idesc_qk, k != 0);
+        }
+        umma_commit(&s_full[t]);
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < num_t; ++t) issue_qk(t, 0);
+
+      for (int j = 0; j < num_kv; ++j) {
+        const int s = j % kKvStages;
+        const uint32_t ph = (j / kKvStages) & 1;
+        const int sn = (j + 1) % kKvStages;
+        const uint32_t phn = ((j + 1) / kKvStages) & 1;
+        for (int t = 0; t < num_t; ++t) {
+          mbar_wait(&p_full[t], j & 1);  // softmax t has read S_t(j) and written P_t(j)
+          tc_fence_after();
+          if (j + 1 < num_kv) {
+            if (t == 0) {
+              mbar_wait(&k_full[sn], phn);
+              tc_fence_after();
+            }
+            issue_qk(t, sn);  // next S first: lets softmax t start on tile j+1 while PV(j) runs
+          }
+          if (t == 0) {
+            mbar_wait(&v_full[s], ph);
+            tc_fence_after();
+          }
+          const uint32_t d = tmem_base + kTmO + t * 64;
+          const uint32_t a = tmem_base + kTmP + t * 64;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t bdesc = make_smem_desc_sw128(v_addr + s * kTileBytes + k * 2048, 1024, 1024);
+            umma_f16_ts(d, a + k * 8, bdesc, idesc_pv, (j | k) != 0);
+          }
+          umma_commit(&pv_done[t]);
+        }
+        umma_commit(&kv_empty[s]);  // both tiles' PV(j) (and QK(j)) have consumed stage s
+      }
+    }
+   }
+  } else {
+    // ===== softmax groups: one thread per query row =====
+    reg_alloc<224>();
+    const int t = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    if (t < num_t) {
+      const uint32_t lane_sel = uint32_t(quarter * 32) << 16;
+      const uint32_t tm_s = tmem_base + lane_sel + kTmS + t * 128;
+      const uint32_t tm_o = tmem_base + lane_sel + kTmO + t * 64;
+      const uint32_t tm_p = tmem_base + lane_sel + kTmP + t * 64;
+      const int row_in_cta = t * 128 + quarter * 32 + lane;
+      const float sc = p.scale_log2;
+      float m_used = -INFINITY;  // running max (scaled, log2 domain) the stored exponents are relative to
+      float l = 0.f;
+
+      for (int j = 0; j < num_kv; ++j) {
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        uint32_t sr[128];
+        tmem_ld_x32(tm_s, sr);
+        tmem_ld_x32(tm_s + 32, sr + 32);
+        tmem_ld_x32(tm_s + 64, sr + 64);
+        tmem_ld_x32(tm_s + 96, sr + 96);
+        tmem_ld_wait();
+
+        const int kv_valid = p.seq_len - j * 128;
+        if (kv_valid < 128) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c >= kv_valid) sr[c] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+        }
+        const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+
+        if (j == 0) {
+          m_used = m_tile;
+        } else {
+          // P_t(j-1) must have been consumed and O_t must be quiescent before we touch either
+          mbar_wait(&pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+          const bool grow = m_tile > m_used + 8.0f;
+          if (__any_sync(0xffffffffu, grow)) {
+            float alpha = 1.0f;
+            if (grow) {
+              alpha = fast_exp2(m_used - m_tile);
+              m_used = m_tile;
+            }
+            l *= alpha;
+            uint32_t o[32];
+#pragma unroll
+            for (int hcol = 0; hcol < 64; hcol += 32) {
+              tmem_ld_x32(tm_o + hcol, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              tmem_st_x32(tm_o + hcol, o);
+            }
+            tmem_st_wait();
+          }
+        }
+
+        const float neg_m = -m_used;
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 128; c += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c]), sc, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + 1]), sc, neg_m));
+          sum0 += p0;
+          sum1 += p1;
+          sr[c >> 1] = pack_bf16x2(p0, p1);
+        }
+        l += sum0 + sum1;
+        tmem_st_x32(tm_p, sr);
+        tmem_st_x32(tm_p + 32, sr + 32);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+      }
+
+      // epilogue: O / l -> bf16 -> HBM
+      mbar_wait(&pv_done[t], (num_kv - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      const bool row_ok = row_in_cta < q_valid;
+      __nv_bfloat16* orow = p.out + size_t(row_base + q0 + row_in_cta) * p.ldo + head * 64;
+#pragma unroll
+      for (int hcol = 0; hcol < 64; hcol += 32) {
+        uint32_t o[32];
+        tmem_ld_x32(tm_o + hcol, o);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+            v.y = pack_bf16x2(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+            v.z = pack_bf16x2(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+            v.w = pack_bf16x2(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + hcol + c) = v;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace pi3b
+
+using namespace pi3b;
+
+extern "C" int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
+                                  int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo,
+                                  int num_seqs, int seq_len, int num_heads, float scale) {
+  PI3B_REQUIRE(q && k && v && out, "pi3b_attn_fwd_hd64: null pointer");
+  PI3B_REQUIRE(num_seqs > 0 && seq_len > 0 && num_heads > 0, "pi3b_attn_fwd_hd64: bad shape");
+  PI3B_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+               "pi3b_attn_fwd_hd64: row pitches must be multiples of 8 elements");
+  PI3B_REQUIRE(q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0, "pi3b_attn_fwd_hd64: column offsets %% 8");
+  PI3B_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "pi3b_attn_fwd_hd64: out must be 16-byte aligned");
+  const uint64_t rows = uint64_t(num_seqs) * seq_len;
+  PI3B_REQUIRE(rows < (1ull << 31), "pi3b_attn_fwd_hd64: too many rows");
+  const int64_t items = int64_t((seq_len + 255) / 256) * num_seqs * num_heads;
+  PI3B_REQUIRE(items < (1ll << 31), "pi3b_attn_fwd_hd64: too many work items");
+
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_tmap_2d(&tmQ, q, 0, rows, uint64_t(q_col0) + 64ull * num_heads, uint64_t(ldq) * 2, 128, 64))) return rc;
+  if ((rc = make_tmap_2d(&tmK, k, 0, rows, uint64_t(k_col0) + 64ull * num_heads, uint64_t(ldk) * 2, 128, 64))) return rc;
+  if ((rc = make_tmap_2d(&tmV, v, 0, rows, uint64_t(v_col0) + 64ull * num_heads, uint64_t(ldv) * 2, 128, 64))) return rc;
+
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL) !=
+        cudaSuccess)
+      return check_launch("attn: cudaFuncSetAttribute");
+    configured = true;
+  }
+  AttnParams p;
+  p.num_seqs = num_seqs; p.seq_len = seq_len; p.num_heads = num_heads;
+  p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = (int)ldo;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  attn_fwd_kernel<<<(unsigned)items, kAttnThreads, AttnSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  return check_launch("attn launch");
+}

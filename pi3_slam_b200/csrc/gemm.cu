@@ -25,6 +25,7 @@ struct GemmParams {
   int ldo, ld_resid;
   int out_f32;  // 1: fp32 output, 0: bf16 output
   int act;      // 0 none, 1 GELU(erf), 2 ReLU
+  int vec_ok;   // 1: out/resid/bias/gamma satisfy the 16-byte vector-path alignment
 };
 
 constexpr int kBlockM = 128;
@@ -171,7 +172,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (nvalid == 32) {
+        if (nvalid == 32 && p.vec_ok) {
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -290,12 +291,10 @@ extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda,
   const int esz = in_dtype == 0 ? 2 : 4;
   PI3B_REQUIRE((lda * esz) % 16 == 0 && (ldw * esz) % 16 == 0, "pi3b_gemm: lda/ldw must give 16-byte row pitch");
   PI3B_REQUIRE(lda >= K && ldw >= K, "pi3b_gemm: lda/ldw < K");
-  PI3B_REQUIRE(ldo % (out_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-               "pi3b_gemm: output must be 16-byte aligned with ldo %% %d == 0", out_f32 ? 4 : 8);
-  PI3B_REQUIRE(!resid || (ld_resid % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0),
-               "pi3b_gemm: resid must be 16-byte aligned with ld %% 4 == 0");
-  PI3B_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "pi3b_gemm: bias must be 16-byte aligned");
-  PI3B_REQUIRE(!gamma || (reinterpret_cast<uintptr_t>(gamma) & 15) == 0, "pi3b_gemm: gamma must be 16-byte aligned");
+  PI3B_REQUIRE(ldo >= N && (!resid || ld_resid >= N), "pi3b_gemm: ldo/ld_resid < N");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int vec_ok = (ldo % (out_f32 ? 4 : 8) == 0) && al16(out) && (!resid || (ld_resid % 4 == 0 && al16(resid))) &&
+                     (!bias || al16(bias)) && (!gamma || al16(gamma));
 
   const int num_sms = cached_num_sms();
   const int block_k = 128 / esz;
@@ -313,7 +312,7 @@ extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda,
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.gamma = gamma; p.resid = resid;
   p.out = out; p.ldo = (int)ldo; p.ld_resid = (int)ld_resid;
-  p.out_f32 = out_f32; p.act = act;
+  p.out_f32 = out_f32; p.act = act; p.vec_ok = vec_ok;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (in_dtype == 0) {
     return wide ? launch_gemm<256, 4, false>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, false>(tmA, tmB, p, num_sms, st);

@@ -57,3 +57,23 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
                        1 if out.dtype == torch.float32 else 0, act)
     _lib.check(rc, "pi3b_gemm")
     return out
+
+
+def attention_qkv(qkv: torch.Tensor, out: torch.Tensor, num_seqs: int, seq_len: int, num_heads: int = 16,
+                  scale: float = 0.125) -> torch.Tensor:
+    """softmax(q k^T * scale) v per (sequence, head), head_dim 64.
+
+    qkv: bf16 [num_seqs*seq_len, 3*num_heads*64] packed as the qkv Linear emits it (q | k | v, head-major
+    inside each third — reference layout, pi3/models/layers/attention.py:326-329). out: bf16
+    [num_seqs*seq_len, num_heads*64].
+    """
+    lib = _lib.load()
+    _req(qkv, torch.bfloat16, "qkv"); _req(out, torch.bfloat16, "out")
+    C = num_heads * 64
+    assert qkv.dim() == 2 and qkv.shape[1] == 3 * C and qkv.stride(1) == 1
+    assert qkv.shape[0] == num_seqs * seq_len and out.shape[0] == qkv.shape[0] and out.shape[1] == C
+    ld = qkv.stride(0)
+    rc = lib.pi3b_attn_fwd_hd64(_stream(), qkv.data_ptr(), qkv.data_ptr(), qkv.data_ptr(), ld, ld, ld, 0, C, 2 * C,
+                                out.data_ptr(), out.stride(0), num_seqs, seq_len, num_heads, scale)
+    _lib.check(rc, "pi3b_attn_fwd_hd64")
+    return out
