@@ -1,0 +1,135 @@
+/*
+ * pi3b200.h — C ABI of libpi3b200.so: the B200 (sm_100a) kernels behind Pi3_SLAM's offline chunk-creation
+ * hot path. This is the drop-in boundary: plain pointers and sizes, no torch types.
+ *
+ * Conventions (all entry points):
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and the call returns
+ *     immediately. No entry point synchronises, allocates device memory or throws.
+ *   - every pointer is a DEVICE pointer unless marked "host".
+ *   - matrices are row-major with unit inner stride; `ld*` are row pitches in ELEMENTS.
+ *   - return value: 0 = ok; -1 bad argument; -2 CUDA launch/runtime error; -3 driver (TMA descriptor) error.
+ *     pi3b_last_error() returns a thread-local message for the last failing call on this thread.
+ *   - thread-safe for concurrent calls on distinct streams.
+ *
+ * "replaces:" cites the reference interface (file:line in urbste/Pi3_SLAM) each entry point stands in for.
+ */
+#ifndef PI3B200_H_
+#define PI3B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int pi3b_version(void);
+const char* pi3b_last_error(void);
+
+/* out[M,N] = [resid +] gamma * act(A[M,K] * W[N,K]^T + bias)      (tcgen05 tensor cores, fp32 accumulate)
+ * in_dtype 0: A, W bf16 (kind::f16); 1: A, W fp32 consumed as TF32 (kind::tf32).
+ * bias, gamma: fp32 [N] or NULL. resid: fp32 [.., ld_resid] or NULL, may alias out. out: fp32 (out_f32=1) or bf16.
+ * act: 0 none, 1 GELU(erf), 2 ReLU. Row remap (grp_in > 0): GEMM row m is written to / reads resid from row
+ * (m / grp_in) * grp_out + grp_off + m % grp_in. lda/ldw must give 16-byte row pitches.
+ * replaces: every nn.Linear on the path — pi3/models/layers/attention.py:256-258 (qkv, proj),
+ *   pi3/models/dinov2/layers/mlp.py:29-31 (fc1+GELU, fc2), pi3/models/dinov2/layers/layer_scale.py:26-27 and
+ *   the residual adds of pi3/models/layers/block.py:333-334 (fused), pi3/models/layers/transformer_head.py:24,46,68,
+ *   pi3/models/layers/camera_head.py:21-23,40-46, and the patch-embed conv pi3/models/dinov2/layers/patch_embed.py:65,75. */
+int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+              const float* bias, const float* gamma, const float* resid, int64_t ld_resid, void* out, int64_t ldo,
+              int out_f32, int act, int grp_in, int grp_out, int grp_off);
+
+/* out = softmax(q k^T * scale) v, head_dim 64, bf16, per (sequence, head). Rows of sequence s are
+ * [s*seq_len, (s+1)*seq_len); head h lives at columns {q,k,v}_col0 + 64*h of its operand; out at column 64*h.
+ * replaces: F.scaled_dot_product_attention at pi3/models/layers/attention.py:102-104 and :336-338
+ *   (frame-local and chunk-global attention of pi3/models/pi3.py:156-166). */
+int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
+                       int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo, int num_seqs,
+                       int seq_len, int num_heads, float scale);
+
+/* out[M,1024] = LayerNorm(x[M,1024]) * gamma + beta (fp32 in; bf16 or fp32 out; in place allowed).
+ * If override_rows != NULL, rows r with r % period < n_override are set to override_rows[r % period] instead.
+ * replaces: nn.LayerNorm(eps=1e-6) in pi3/models/dinov2/layers/block.py:88-113, pi3/models/layers/block.py:310-335,
+ *   encoder norm + token slicing pi3/models/dinov2/models/vision_transformer.py:271-275 and the register-token
+ *   concat of pi3/models/pi3.py:140-144. */
+int pi3b_layernorm(void* stream, const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                   void* out, int64_t ldo, int out_f32, int M, int D, const float* override_rows, int period,
+                   int n_override);
+
+/* In place on the q and k thirds of packed qkv [M, 3*64*heads] bf16: optional LayerNorm(64) (q/k-norm params
+ * fp32 [64], all four NULL to skip) then 2-D RoPE (do_rope) with cs_table fp32 [table_rows][16][2] = (cos, sin) of
+ * pos * base^(-j/16). Token t = row % tokens_per_frame; t < n_special => position (0,0) (identity);
+ * otherwise (y, x) = ((t-n_special) / patch_w + 1, (t-n_special) % patch_w + 1).
+ * replaces: q_norm/k_norm + rope of pi3/models/layers/attention.py:330-334, RoPE2D pi3/models/layers/pos_embed.py:112-159,
+ *   PositionGetter :162-174, and the reference's only native kernel rope_2d_cuda_kernel pi3/models/curope/kernels.cu:17-108
+ *   (pybind rope_2d, pi3/models/curope/curope.cpp:49-69). */
+int pi3b_qknorm_rope(void* stream, void* qkv, int64_t ld, int M, int num_heads, int tokens_per_frame, int n_special,
+                     int patch_w, const float* qn_w, const float* qn_b, const float* kn_w, const float* kn_b, float eps,
+                     const float* cs_table, int table_rows, int do_rope);
+
+/* imgs fp32 [N,3,H,W] in [0,1] -> out bf16 [N*(H/14)*(W/14), ldk]: normalised ((x-mean)/std) im2col of the 14x14/s14
+ * patch conv, column c*196 + 14*i + j, columns [588, ldk) zero. mean3/std3: HOST pointers to 3 floats.
+ * replaces: pi3/models/pi3.py:174 + the input side of pi3/models/dinov2/layers/patch_embed.py:68-81. */
+int pi3b_patch_pack(void* stream, const float* imgs, void* out, int N, int H, int W, int ldk, const float* mean3,
+                    const float* std3);
+
+/* out[g, r, :] = table[r, :] for g < num_groups (fp32, D % 4 == 0).
+ * replaces: cls / register / pos-embed token assembly pi3/models/dinov2/models/vision_transformer.py:215-234. */
+int pi3b_broadcast_rows(void* stream, const float* table, float* out, int num_groups, int rows_per_group, int D);
+
+/* fp32 [M,C] -> bf16 [M,C] with independent row pitches (C % 4 == 0).
+ * replaces: the autocast input casts of nn.Linear and the torch.cat of pi3/models/pi3.py:168-171. */
+int pi3b_cast_f32_bf16(void* stream, const float* x, int64_t ldx, void* out, int64_t ldo, int M, int C);
+
+/* Head unpatchify: local_points[n,y,x,:] = (fx*e^fz, fy*e^fz, e^fz), points = R local + t, conf = raw logit, where
+ * f*[..] = feat[n*tokens_per_frame + n_special + (y/14)*(W/14) + x/14][c*196 + 14*(y%14) + x%14]. poses: fp32 [N,4,4].
+ * replaces: LinearPts3d pixel_shuffle pi3/models/layers/transformer_head.py:76-81 and pi3/models/pi3.py:194-209. */
+int pi3b_unpatchify_points_conf(void* stream, const float* feat_pts, int64_t ld_pts, const float* feat_conf,
+                                int64_t ld_conf, const float* poses, float* local_points, float* points, float* conf,
+                                int N, int H, int W, int tokens_per_frame, int n_special);
+
+/* out[n, c] = mean over patch tokens t >= n_special of x[n*tokens_per_frame + t, c].
+ * replaces: AdaptiveAvgPool2d in pi3/models/layers/camera_head.py:55. */
+int pi3b_meanpool_tokens(void* stream, const float* x, int64_t ldx, float* out, int N, int C, int tokens_per_frame,
+                         int n_special);
+
+/* poses[n] = [[R, t], [0,0,0,1]] with R = the rotation nearest to the row-normalised 3x3 rot9[n] (fp64 solve).
+ * replaces: svd_orthogonalize / convert_pose_to_4x4 pi3/models/layers/camera_head.py:66-93 (torch.svd + torch.det). */
+int pi3b_pose_from_9d(void* stream, const float* rot9, int64_t ld_r, const float* trans, int64_t ld_t, float* poses,
+                      int N);
+
+/* mask[n,y,x] = sigmoid(conf) > conf_thr && !((max3x3 z - min3x3 z) / z > rtol); z read with element stride z_stride.
+ * replaces: OfflineChunkCreator._compute_masks slam/offline_chunk_creator.py:114-119 + depth_edge pi3/utils/geometry.py:347-375. */
+int pi3b_mask_depth_edge(void* stream, const float* z, int z_stride, const float* conf, uint8_t* mask, int N, int H,
+                         int W, float conf_thr, float rtol);
+
+/* Sample dense maps at keypoints [N,K,2] (x,y): grid_sample(align_corners=False, border) semantics with
+ * g = 2*x/(W-1) - 1; bilinear for points / local_points [N,H,W,3] and images [N,3,H,W] (x255 -> uint8, may be NULL),
+ * nearest for conf [N,H,W] and mask [N,H,W] (uint8).
+ * replaces: _interpolate_world_points_for_keypoints slam/offline_chunk_creator.py:129-159 and
+ *   GridKeypointExtractor._interpolate_colors utils/keypoint_extraction.py:207-229 (CPU grid_sample after a dense D2H). */
+int pi3b_keypoint_gather(void* stream, const float* points, const float* local_points, const float* conf,
+                         const uint8_t* mask, const float* images, const float* keypoints, float* out_points,
+                         float* out_local, float* out_conf, uint8_t* out_mask, uint8_t* out_colors, int N, int K, int H,
+                         int W);
+
+/* out_pts[n, i*ws + j, :] = local_points[n, ys[i], xs[j], :]; out_valid = sigmoid(conf) > conf_thr.
+ * replaces: the nearest F.interpolate to 64x64 in recover_focal_shift utils/geometry_torch.py:140-142. */
+int pi3b_sample_grid(void* stream, const float* local_points, const float* conf, const int* ys, const int* xs,
+                     float* out_pts, uint8_t* out_valid, int N, int H, int W, int hs, int ws, float conf_thr);
+
+/* out2[0] = lower median of a[i*a_stride] / b[i*b_stride] over mask[i] != 0, out2[1] = count.
+ * replaces: _get_scale_factor_for_pi3 slam/offline_chunk_creator.py:121-127 (boolean indexing + torch.median). */
+int pi3b_median_ratio(void* stream, const float* a, int a_stride, const float* b, int b_stride, const uint8_t* mask,
+                      int n, float* out2);
+
+/* Batched closed-form similarity (Umeyama): per problem p, (s,R,t) minimising sum |ref - (s R qry + t)|^2 over
+ * valid[p,i] != 0 (valid may be NULL). qry, ref: fp32 [P, n_per, 3]. out18[p] = 4x4 row-major [sR|t], scale, count.
+ * replaces: pt.sfm.OptimizeAlignmentSim3(points_qry, points_ref, perform_optimization=False) +
+ *   pt.math.Sim3d.exp(...).matrix() at utils/reconstruction_alignment.py:89-105 (un-vendored pytheia==0.2.9). */
+int pi3b_umeyama_sim3_batched(void* stream, const float* qry, const float* ref, const uint8_t* valid,
+                              int num_problems, int n_per, float* out18);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PI3B200_H_ */

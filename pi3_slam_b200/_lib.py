@@ -17,10 +17,40 @@ _P = c_void_p
 SIGNATURES = {
     "pi3b_version": (c_int, []),
     "pi3b_last_error": (c_char_p, []),
+    # stream, in_dtype, A, lda, W, ldw, M, N, K, bias, gamma, resid, ld_resid, out, ldo, out_f32, act, grp_in, grp_out, grp_off
     "pi3b_gemm": (c_int, [_P, c_int, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, _P,
-                          c_int64, c_int, c_int]),
+                          c_int64, c_int, c_int, c_int, c_int, c_int]),
+    # stream, q, k, v, ldq, ldk, ldv, q_col0, k_col0, v_col0, out, ldo, num_seqs, seq_len, num_heads, scale
     "pi3b_attn_fwd_hd64": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64,
                                    c_int, c_int, c_int, c_float]),
+    # stream, x, ldx, gamma, beta, eps, out, ldo, out_f32, M, D, override_rows, period, n_override
+    "pi3b_layernorm": (c_int, [_P, _P, c_int64, _P, _P, c_float, _P, c_int64, c_int, c_int, c_int, _P, c_int, c_int]),
+    # stream, qkv, ld, M, heads, tokens_per_frame, n_special, patch_w, qn_w, qn_b, kn_w, kn_b, eps, cs_table, table_rows, do_rope
+    "pi3b_qknorm_rope": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_float, _P,
+                                 c_int, c_int]),
+    # stream, imgs, out, N, H, W, ldk, mean3(host), std3(host)
+    "pi3b_patch_pack": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    # stream, table, out, num_groups, rows_per_group, D
+    "pi3b_broadcast_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int]),
+    # stream, feat_pts, ld_pts, feat_conf, ld_conf, poses, local_points, points, conf, N, H, W, tokens_per_frame, n_special
+    "pi3b_unpatchify_points_conf": (c_int, [_P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
+                                            c_int]),
+    # stream, x, ldx, out, ldo, M, C
+    "pi3b_cast_f32_bf16": (c_int, [_P, _P, c_int64, _P, c_int64, c_int, c_int]),
+    # stream, x, ldx, out, N, C, tokens_per_frame, n_special
+    "pi3b_meanpool_tokens": (c_int, [_P, _P, c_int64, _P, c_int, c_int, c_int, c_int]),
+    # stream, rot9, ld_r, trans, ld_t, poses, N
+    "pi3b_pose_from_9d": (c_int, [_P, _P, c_int64, _P, c_int64, _P, c_int]),
+    # stream, z, z_stride, conf, mask, N, H, W, conf_thr, rtol
+    "pi3b_mask_depth_edge": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_float, c_float]),
+    # stream, points, local_points, conf, mask, images, keypoints, out_points, out_local, out_conf, out_mask, out_colors, N, K, H, W
+    "pi3b_keypoint_gather": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int]),
+    # stream, local_points, conf, ys, xs, out_pts, out_valid, N, H, W, hs, ws, conf_thr
+    "pi3b_sample_grid": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float]),
+    # stream, a, a_stride, b, b_stride, mask, n, out2
+    "pi3b_median_ratio": (c_int, [_P, _P, c_int, _P, c_int, _P, c_int, _P]),
+    # stream, qry, ref, valid, num_problems, n_per, out18
+    "pi3b_umeyama_sim3_batched": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
 }
 
 

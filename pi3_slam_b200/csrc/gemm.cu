@@ -26,6 +26,9 @@ struct GemmParams {
   int out_f32;  // 1: fp32 output, 0: bf16 output
   int act;      // 0 none, 1 GELU(erf), 2 ReLU
   int vec_ok;   // 1: out/resid/bias/gamma satisfy the 16-byte vector-path alignment
+  // output-row remap: GEMM row m lands in row (m / grp_in) * grp_out + grp_off + m % grp_in of out/resid
+  // (grp_in == 0: identity). Used to scatter patch rows between the per-frame special tokens.
+  int grp_in, grp_out, grp_off;
 };
 
 constexpr int kBlockM = 128;
@@ -156,8 +159,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      const int m = m_blk * kBlockM + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
+      const int m_in = m_blk * kBlockM + quarter * 32 + lane;
+      const bool row_ok = m_in < p.M;
+      const int m = p.grp_in ? (m_in / p.grp_in) * p.grp_out + p.grp_off + m_in % p.grp_in : m_in;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -283,11 +287,12 @@ using namespace pi3b;
 // See include/pi3b200.h for the contract.
 extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda, const void* W, int64_t ldw, int M,
                          int N, int K, const float* bias, const float* gamma, const float* resid, int64_t ld_resid,
-                         void* out, int64_t ldo, int out_f32, int act) {
+                         void* out, int64_t ldo, int out_f32, int act, int grp_in, int grp_out, int grp_off) {
   PI3B_REQUIRE(A && W && out, "pi3b_gemm: null pointer");
   PI3B_REQUIRE(M > 0 && N > 0 && K > 0, "pi3b_gemm: bad shape M=%d N=%d K=%d", M, N, K);
   PI3B_REQUIRE(in_dtype == 0 || in_dtype == 1, "pi3b_gemm: in_dtype must be 0 (bf16) or 1 (fp32->tf32)");
   PI3B_REQUIRE(act >= 0 && act <= 2, "pi3b_gemm: act must be 0/1/2");
+  PI3B_REQUIRE(grp_in == 0 || (grp_in > 0 && grp_out >= grp_in + grp_off && grp_off >= 0), "pi3b_gemm: bad row remap");
   const int esz = in_dtype == 0 ? 2 : 4;
   PI3B_REQUIRE((lda * esz) % 16 == 0 && (ldw * esz) % 16 == 0, "pi3b_gemm: lda/ldw must give 16-byte row pitch");
   PI3B_REQUIRE(lda >= K && ldw >= K, "pi3b_gemm: lda/ldw < K");
@@ -313,6 +318,7 @@ extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda,
   p.bias = bias; p.gamma = gamma; p.resid = resid;
   p.out = out; p.ldo = (int)ldo; p.ld_resid = (int)ld_resid;
   p.out_f32 = out_f32; p.act = act; p.vec_ok = vec_ok;
+  p.grp_in = grp_in; p.grp_out = grp_out; p.grp_off = grp_off;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (in_dtype == 0) {
     return wide ? launch_gemm<256, 4, false>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, false>(tmA, tmB, p, num_sms, st);

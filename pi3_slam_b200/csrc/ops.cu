@@ -232,6 +232,19 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict
   conf[gid] = fconf[trow * ld_conf + inner];
 }
 
+// fp32 -> bf16 cast of a [M, C] matrix with independent row pitches (decoder taps -> concat buffer,
+// pi3.py:168-171; fp32 residual -> bf16 GEMM operand, as autocast does for nn.Linear inputs).
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, int64_t ldx,
+                                                        __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t M,
+                                                        int C4) {
+  const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= M * C4) return;
+  const int64_t row = gid / C4;
+  const int c = int(gid % C4);
+  const float4 v = *reinterpret_cast<const float4*>(x + row * ldx + c * 4);
+  *reinterpret_cast<uint2*>(out + row * ldo + c * 4) = make_uint2(bf16x2(v.x, v.y), bf16x2(v.z, v.w));
+}
+
 // Mean over the patch tokens of each frame (camera_head.py:55): x fp32 [N*T, C] -> out [N, C].
 __global__ void __launch_bounds__(256) meanpool_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ out,
                                                        int C, int tokens_per_frame, int n_special) {
@@ -445,6 +458,14 @@ extern "C" int pi3b_unpatchify_points_conf(void* stream, const float* feat_pts, 
   unpatchify_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       feat_pts, ld_pts, feat_conf, ld_conf, poses, local_points, points, conf, N, H, W, tokens_per_frame, n_special);
   return check_launch("unpatchify launch");
+}
+
+extern "C" int pi3b_cast_f32_bf16(void* stream, const float* x, int64_t ldx, void* out, int64_t ldo, int M, int C) {
+  PI3B_REQUIRE(x && out && M > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "pi3b_cast_f32_bf16: bad args");
+  const int64_t total = int64_t(M) * (C / 4);
+  cast_bf16_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, static_cast<__nv_bfloat16*>(out), ldo, M, C / 4);
+  return check_launch("cast launch");
 }
 
 extern "C" int pi3b_meanpool_tokens(void* stream, const float* x, int64_t ldx, float* out, int N, int C,

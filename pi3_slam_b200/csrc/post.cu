@@ -1,0 +1,327 @@
+// Post-processing kernels of the chunk path: keypoint gather (bilinear / nearest grid sampling on the
+// device instead of the reference's 350-550 MB D2H + CPU grid_sample), lower-median of a masked ratio
+// (MoGe metric scale), strided sample gather for the intrinsics solve, and the batched Umeyama Sim3.
+#include "host_common.h"
+
+#include <math.h>
+
+namespace pi3b {
+
+// ------------------------------------------------------------------------------------------------
+// Keypoint gather. Reference: offline_chunk_creator.py:129-159 and keypoint_extraction.py:207-229:
+//   g = (x / (W-1)) * 2 - 1;  F.grid_sample(align_corners=False, padding_mode='border')
+//   => source coordinate ix = ((g + 1) * W - 1) / 2 clipped to [0, W-1]; bilinear for points,
+//   local_points and colours (x255, truncated to uint8), nearest (round-half-even) for conf and mask.
+// One thread per (frame, keypoint); the arithmetic follows ATen's fp32 op order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float src_index(float coord, int size) {
+  const float g = __fsub_rn(__fmul_rn(__fdiv_rn(coord, float(size - 1)), 2.0f), 1.0f);
+  float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), float(size)), 1.0f), 2.0f);
+  ix = fminf(float(size - 1), fmaxf(ix, 0.0f));
+  return ix;
+}
+
+__global__ void __launch_bounds__(128) keypoint_gather_kernel(
+    const float* __restrict__ points, const float* __restrict__ local_points, const float* __restrict__ conf,
+    const uint8_t* __restrict__ mask, const float* __restrict__ images, const float* __restrict__ kps,
+    float* __restrict__ o_points, float* __restrict__ o_local, float* __restrict__ o_conf, uint8_t* __restrict__ o_mask,
+    uint8_t* __restrict__ o_colors, int N, int K, int H, int W) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= N * K) return;
+  const int n = gid / K;
+  const float ix = src_index(kps[gid * 2 + 0], W);
+  const float iy = src_index(kps[gid * 2 + 1], H);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const int x0 = int(x0f), y0 = int(y0f), x1 = x0 + 1, y1 = y0 + 1;
+  const float w_nw = __fmul_rn(__fsub_rn(x0f + 1.0f, ix), __fsub_rn(y0f + 1.0f, iy));
+  const float w_ne = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(y0f + 1.0f, iy));
+  const float w_sw = __fmul_rn(__fsub_rn(x0f + 1.0f, ix), __fsub_rn(iy, y0f));
+  const float w_se = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(iy, y0f));
+  const bool in_x0 = x0 >= 0 && x0 < W, in_x1 = x1 >= 0 && x1 < W;
+  const bool in_y0 = y0 >= 0 && y0 < H, in_y1 = y1 >= 0 && y1 < H;
+  const size_t fbase = size_t(n) * H * W;
+
+  auto bil = [&](const float* src, size_t stride) {
+    float acc = 0.f;
+    if (in_y0 && in_x0) acc = __fadd_rn(acc, __fmul_rn(src[(size_t(y0) * W + x0) * stride], w_nw));
+    if (in_y0 && in_x1) acc = __fadd_rn(acc, __fmul_rn(src[(size_t(y0) * W + x1) * stride], w_ne));
+    if (in_y1 && in_x0) acc = __fadd_rn(acc, __fmul_rn(src[(size_t(y1) * W + x0) * stride], w_sw));
+    if (in_y1 && in_x1) acc = __fadd_rn(acc, __fmul_rn(src[(size_t(y1) * W + x1) * stride], w_se));
+    return acc;
+  };
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o_points[gid * 3 + c] = bil(points + fbase * 3 + c, 3);
+    o_local[gid * 3 + c] = bil(local_points + fbase * 3 + c, 3);
+    if (images) {
+      const float col = bil(images + (size_t(n) * 3 + c) * H * W, 1);
+      o_colors[gid * 3 + c] = static_cast<uint8_t>(__fmul_rn(col, 255.0f));  // .to(torch.uint8) truncates
+    }
+  }
+  const int xn = int(nearbyintf(ix)), yn = int(nearbyintf(iy));
+  const bool in_n = xn >= 0 && xn < W && yn >= 0 && yn < H;
+  o_conf[gid] = in_n ? conf[fbase + size_t(yn) * W + xn] : 0.f;
+  o_mask[gid] = in_n ? (mask[fbase + size_t(yn) * W + xn] != 0) : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strided sample gather for the intrinsics solve (geometry_torch.py:140-142: nearest F.interpolate of
+// local_points / mask to 64x64). out_pts [N, hs*ws, 3], out_valid [N, hs*ws] (sigmoid(conf) > thr).
+// ------------------------------------------------------------------------------------------------
+__global__ void sample_grid_kernel(const float* __restrict__ local_points, const float* __restrict__ conf,
+                                   const int* __restrict__ ys, const int* __restrict__ xs, float* __restrict__ out_pts,
+                                   uint8_t* __restrict__ out_valid, int N, int H, int W, int hs, int ws, float thr) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= N * hs * ws) return;
+  const int n = gid / (hs * ws);
+  const int r = gid % (hs * ws);
+  const int y = ys[r / ws], x = xs[r % ws];
+  const size_t pix = (size_t(n) * H + y) * W + x;
+  out_pts[gid * 3 + 0] = local_points[pix * 3 + 0];
+  out_pts[gid * 3 + 1] = local_points[pix * 3 + 1];
+  out_pts[gid * 3 + 2] = local_points[pix * 3 + 2];
+  out_valid[gid] = (1.0f / (1.0f + expf(-conf[pix]))) > thr ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lower median of a[i] / b[i] over mask[i] != 0 (offline_chunk_creator.py:121-127: torch.median returns
+// the lower of the two middle elements). Exact radix select on the order-preserving uint32 key of the fp32
+// ratio: 4 passes of 256-bin histograms, single block (the input is one frame, ~1e5 elements).
+// out[0] = median (NaN if the mask is empty), out[1] = count.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(1024) median_ratio_kernel(const float* __restrict__ a, int a_stride,
+                                                            const float* __restrict__ b, int b_stride,
+                                                            const uint8_t* __restrict__ mask, int n,
+                                                            float* __restrict__ out) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_rank, s_count;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  unsigned int local = 0;
+  for (int i = tid; i < n; i += blockDim.x) local += mask[i] != 0;
+  atomicAdd(&s_count, local);
+  __syncthreads();
+  const unsigned int count = s_count;
+  if (count == 0) {
+    if (tid == 0) { out[0] = __int_as_float(0x7fc00000); out[1] = 0.f; }
+    return;
+  }
+  // NaN ratios sort last in torch.median's ordering; map them to the largest key
+  if (tid == 0) { s_prefix = 0; s_rank = (count - 1) / 2; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    const unsigned int hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = tid; i < n; i += blockDim.x) {
+      if (!mask[i]) continue;
+      const float r = a[size_t(i) * a_stride] / b[size_t(i) * b_stride];
+      const uint32_t key = isnan(r) ? 0xffffffffu : float_key(r);
+      if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int rank = s_rank, acc = 0;
+      int bin = 0;
+      for (; bin < 256; ++bin) {
+        if (acc + hist[bin] > rank) break;
+        acc += hist[bin];
+      }
+      s_rank = rank - acc;
+      s_prefix = prefix | (static_cast<unsigned int>(bin) << shift);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out[0] = s_prefix == 0xffffffffu ? __int_as_float(0x7fc00000) : key_float(s_prefix);
+    out[1] = float(count);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched Umeyama similarity (Umeyama 1991): for each problem b find (s, R, t) minimising
+// sum_i w_i | ref_i - (s R qry_i + t) |^2 over the valid correspondences. Stands in for pytheia's
+// OptimizeAlignmentSim3(points_qry, points_ref, perform_optimization=False)
+// (utils/reconstruction_alignment.py:89-105): maps QUERY-chunk points onto REFERENCE-chunk points.
+// One block per problem, fp64 accumulation; R = U diag(1,1,det(UV^T)) V^T of the 3x3 covariance from a
+// Jacobi eigen-solve. Output per problem: 4x4 row-major [sR | t; 0 0 0 1] + scale + #valid.
+// ------------------------------------------------------------------------------------------------
+__device__ void jacobi_eig3_d(double A[3][3], double V[3][3]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (fabs(A[p][q]) < 1e-300) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int tid = threadIdx.x;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double tot = 0;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+  return tot;
+}
+
+__global__ void __launch_bounds__(256) umeyama_kernel(const float* __restrict__ qry, const float* __restrict__ ref,
+                                                      const uint8_t* __restrict__ valid, int n_per,
+                                                      float* __restrict__ out) {
+  __shared__ double red[8];
+  const int b = blockIdx.x;
+  const float* q = qry + size_t(b) * n_per * 3;
+  const float* r = ref + size_t(b) * n_per * 3;
+  const uint8_t* v = valid ? valid + size_t(b) * n_per : nullptr;
+  double cnt = 0, mq[3] = {0, 0, 0}, mr[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < n_per; i += blockDim.x) {
+    if (v && !v[i]) continue;
+    cnt += 1;
+    for (int c = 0; c < 3; ++c) { mq[c] += q[i * 3 + c]; mr[c] += r[i * 3 + c]; }
+  }
+  cnt = block_sum(cnt, red);
+  for (int c = 0; c < 3; ++c) { mq[c] = block_sum(mq[c], red); mr[c] = block_sum(mr[c], red); }
+  float* o = out + size_t(b) * 18;
+  if (cnt < 3) {
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? 1.f : 0.f;
+      o[16] = 1.f; o[17] = float(cnt);
+    }
+    return;
+  }
+  for (int c = 0; c < 3; ++c) { mq[c] /= cnt; mr[c] /= cnt; }
+  double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, varq = 0;  // S = sum (r - mr)(q - mq)^T
+  for (int i = threadIdx.x; i < n_per; i += blockDim.x) {
+    if (v && !v[i]) continue;
+    double dq[3], dr[3];
+    for (int c = 0; c < 3; ++c) { dq[c] = q[i * 3 + c] - mq[c]; dr[c] = r[i * 3 + c] - mr[c]; }
+    varq += dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2];
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) S[a][c] += dr[a] * dq[c];
+  }
+  varq = block_sum(varq, red);
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) S[a][c] = block_sum(S[a][c], red);
+  if (threadIdx.x != 0) return;
+  // SVD of S via eigen-decomposition of S^T S = V diag(sig^2) V^T; u_i = S v_i / sig_i
+  double A[3][3], V[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A[i][j] = S[0][i] * S[0][j] + S[1][i] * S[1][j] + S[2][i] * S[2][j];
+  jacobi_eig3_d(A, V);
+  int ord[3] = {0, 1, 2};
+  for (int i = 0; i < 2; ++i)
+    for (int j = i + 1; j < 3; ++j)
+      if (A[ord[j]][ord[j]] > A[ord[i]][ord[i]]) { const int tmp = ord[i]; ord[i] = ord[j]; ord[j] = tmp; }
+  double v1[3], v2[3], u1[3], u2[3];
+  for (int k = 0; k < 3; ++k) { v1[k] = V[k][ord[0]]; v2[k] = V[k][ord[1]]; }
+  double n1 = 0, n2 = 0;
+  for (int a = 0; a < 3; ++a) {
+    u1[a] = S[a][0] * v1[0] + S[a][1] * v1[1] + S[a][2] * v1[2];
+    u2[a] = S[a][0] * v2[0] + S[a][1] * v2[1] + S[a][2] * v2[2];
+    n1 += u1[a] * u1[a];
+  }
+  n1 = sqrt(n1);
+  for (int a = 0; a < 3; ++a) u1[a] /= n1;
+  const double d12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+  for (int a = 0; a < 3; ++a) { u2[a] -= d12 * u1[a]; n2 += u2[a] * u2[a]; }
+  n2 = sqrt(n2);
+  for (int a = 0; a < 3; ++a) u2[a] /= n2;
+  const double u3[3] = {u1[1] * u2[2] - u1[2] * u2[1], u1[2] * u2[0] - u1[0] * u2[2], u1[0] * u2[1] - u1[1] * u2[0]};
+  const double v3[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
+  // R = [u1 u2 u1xu2][v1 v2 v1xv2]^T (proper rotation; equals U diag(1,1,det) V^T).
+  double R[3][3];
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) R[a][c] = u1[a] * v1[c] + u2[a] * v2[c] + u3[a] * v3[c];
+  // trace(D Sigma) = sig1 + sig2 + d*sig3 with d*sig3 = u3^T S v3 (signed)
+  double s3 = 0;
+  for (int a = 0; a < 3; ++a) s3 += u3[a] * (S[a][0] * v3[0] + S[a][1] * v3[1] + S[a][2] * v3[2]);
+  const double sig1 = sqrt(fmax(A[ord[0]][ord[0]], 0.0)), sig2 = sqrt(fmax(A[ord[1]][ord[1]], 0.0));
+  const double scale = varq > 0 ? (sig1 + sig2 + s3) / varq : 1.0;
+  for (int a = 0; a < 3; ++a) {
+    double t = mr[a];
+    for (int c = 0; c < 3; ++c) {
+      o[a * 4 + c] = float(scale * R[a][c]);
+      t -= scale * R[a][c] * mq[c];
+    }
+    o[a * 4 + 3] = float(t);
+  }
+  o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+  o[16] = float(scale);
+  o[17] = float(cnt);
+}
+
+}  // namespace pi3b
+
+using namespace pi3b;
+
+extern "C" int pi3b_keypoint_gather(void* stream, const float* points, const float* local_points, const float* conf,
+                                    const uint8_t* mask, const float* images, const float* keypoints, float* out_points,
+                                    float* out_local, float* out_conf, uint8_t* out_mask, uint8_t* out_colors, int N,
+                                    int K, int H, int W) {
+  PI3B_REQUIRE(points && local_points && conf && mask && keypoints && out_points && out_local && out_conf && out_mask,
+               "pi3b_keypoint_gather: null pointer");
+  PI3B_REQUIRE(!images || out_colors, "pi3b_keypoint_gather: images given without out_colors");
+  PI3B_REQUIRE(N > 0 && K > 0 && H > 1 && W > 1, "pi3b_keypoint_gather: bad shape");
+  const int total = N * K;
+  keypoint_gather_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      points, local_points, conf, mask, images, keypoints, out_points, out_local, out_conf, out_mask, out_colors, N, K,
+      H, W);
+  return check_launch("keypoint_gather launch");
+}
+
+extern "C" int pi3b_sample_grid(void* stream, const float* local_points, const float* conf, const int* ys,
+                                const int* xs, float* out_pts, uint8_t* out_valid, int N, int H, int W, int hs, int ws,
+                                float conf_thr) {
+  PI3B_REQUIRE(local_points && conf && ys && xs && out_pts && out_valid, "pi3b_sample_grid: null pointer");
+  PI3B_REQUIRE(N > 0 && hs > 0 && ws > 0, "pi3b_sample_grid: bad shape");
+  const int total = N * hs * ws;
+  sample_grid_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      local_points, conf, ys, xs, out_pts, out_valid, N, H, W, hs, ws, conf_thr);
+  return check_launch("sample_grid launch");
+}
+
+extern "C" int pi3b_median_ratio(void* stream, const float* a, int a_stride, const float* b, int b_stride,
+                                 const uint8_t* mask, int n, float* out2) {
+  PI3B_REQUIRE(a && b && mask && out2 && n > 0 && a_stride > 0 && b_stride > 0, "pi3b_median_ratio: bad args");
+  median_ratio_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a, a_stride, b, b_stride, mask, n, out2);
+  return check_launch("median_ratio launch");
+}
+
+extern "C" int pi3b_umeyama_sim3_batched(void* stream, const float* qry, const float* ref, const uint8_t* valid,
+                                         int num_problems, int n_per, float* out18) {
+  PI3B_REQUIRE(qry && ref && out18 && num_problems > 0 && n_per > 0, "pi3b_umeyama_sim3_batched: bad args");
+  umeyama_kernel<<<num_problems, 256, 0, static_cast<cudaStream_t>(stream)>>>(qry, ref, valid, n_per, out18);
+  return check_launch("umeyama launch");
+}

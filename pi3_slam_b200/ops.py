@@ -31,12 +31,13 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
          gamma: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, act: int = ACT_NONE,
-         k: Optional[int] = None) -> torch.Tensor:
+         k: Optional[int] = None, row_remap: Optional[tuple] = None) -> torch.Tensor:
     """out[M,N] = [resid +] gamma * act(a[M,K] @ w[N,K]^T + bias).
 
     a, w: bf16 (tcgen05 kind::f16) or fp32 (read as TF32); row-major with unit inner stride, row pitch
     a multiple of 16 bytes. out: bf16 or fp32. bias/gamma: fp32 [N]. resid: fp32 (may alias out).
-    `k` overrides the contraction length (for K-padded operands).
+    `k` overrides the contraction length (for K-padded operands). `row_remap=(grp_in, grp_out, off)`
+    scatters GEMM row m to row (m // grp_in) * grp_out + off + m % grp_in of out/resid.
     """
     lib = _lib.load()
     assert a.dim() == 2 and w.dim() == 2 and out.dim() == 2
@@ -46,7 +47,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
     M = a.shape[0]
     N = w.shape[0]
     K = k if k is not None else a.shape[1]
-    assert out.shape[0] == M and out.shape[1] == N
+    grp = row_remap if row_remap is not None else (0, 0, 0)
+    m_out = M if row_remap is None else (M // grp[0]) * grp[1]
+    assert out.shape[0] == m_out and out.shape[1] == N
     assert out.dtype in (torch.bfloat16, torch.float32) and out.is_cuda
     for t, nm in ((bias, "bias"), (gamma, "gamma"), (resid, "resid")):
         if t is not None:
@@ -54,7 +57,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
     rc = lib.pi3b_gemm(_stream(), 0 if a.dtype == torch.bfloat16 else 1, a.data_ptr(), a.stride(0), w.data_ptr(),
                        w.stride(0), M, N, K, _ptr(bias), _ptr(gamma), _ptr(resid),
                        resid.stride(0) if resid is not None else 0, out.data_ptr(), out.stride(0),
-                       1 if out.dtype == torch.float32 else 0, act)
+                       1 if out.dtype == torch.float32 else 0, act, grp[0], grp[1], grp[2])
     _lib.check(rc, "pi3b_gemm")
     return out
 
@@ -77,3 +80,194 @@ def attention_qkv(qkv: torch.Tensor, out: torch.Tensor, num_seqs: int, seq_len: 
                                 out.data_ptr(), out.stride(0), num_seqs, seq_len, num_heads, scale)
     _lib.check(rc, "pi3b_attn_fwd_hd64")
     return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out: torch.Tensor,
+              override_rows: Optional[torch.Tensor] = None, period: int = 0) -> torch.Tensor:
+    """out = LayerNorm_1024(x) (fp32 in, bf16 or fp32 out). Rows r with r % period < len(override_rows) are
+    replaced by override_rows[r % period] instead (token re-labelling between encoder and decoder)."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    assert x.dim() == 2 and x.stride(1) == 1 and out.shape == x.shape and out.stride(1) == 1 and out.is_cuda
+    n_ov = 0
+    if override_rows is not None:
+        _req(override_rows, torch.float32, "override_rows")
+        assert override_rows.is_contiguous() and override_rows.shape[1] == x.shape[1]
+        n_ov = override_rows.shape[0]
+    rc = lib.pi3b_layernorm(_stream(), x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), eps,
+                            out.data_ptr(), out.stride(0), 1 if out.dtype == torch.float32 else 0, x.shape[0],
+                            x.shape[1], _ptr(override_rows), period, n_ov)
+    _lib.check(rc, "pi3b_layernorm")
+    return out
+
+
+def qknorm_rope(qkv: torch.Tensor, num_heads: int, tokens_per_frame: int, n_special: int, patch_w: int,
+                cs_table: Optional[torch.Tensor], qn: Optional[tuple] = None, kn: Optional[tuple] = None,
+                eps: float = 1e-5) -> torch.Tensor:
+    """In place on the q and k thirds of packed qkv: optional LayerNorm(64) then RoPE-2D (if cs_table given).
+    cs_table: fp32 [max_pos+1, 16, 2] = (cos, sin) of pos * base^(-j/16)."""
+    lib = _lib.load()
+    _req(qkv, torch.bfloat16, "qkv")
+    assert qkv.dim() == 2 and qkv.stride(1) == 1
+    ptrs = [None, None, None, None]
+    if qn is not None:
+        for t in (*qn, *kn):
+            _req(t, torch.float32, "qk-norm parameter")
+        ptrs = [qn[0].data_ptr(), qn[1].data_ptr(), kn[0].data_ptr(), kn[1].data_ptr()]
+    rows = 0
+    if cs_table is not None:
+        _req(cs_table, torch.float32, "cs_table")
+        assert cs_table.is_contiguous() and cs_table.shape[1:] == (16, 2)
+        rows = cs_table.shape[0]
+    rc = lib.pi3b_qknorm_rope(_stream(), qkv.data_ptr(), qkv.stride(0), qkv.shape[0], num_heads, tokens_per_frame,
+                              n_special, patch_w, *ptrs, eps, _ptr(cs_table), rows, 1 if cs_table is not None else 0)
+    _lib.check(rc, "pi3b_qknorm_rope")
+    return qkv
+
+
+def patch_pack(imgs: torch.Tensor, out: torch.Tensor, mean, std) -> torch.Tensor:
+    """imgs fp32 [N,3,H,W] -> out bf16 [N*P, ldk] (normalised im2col of the 14x14/s14 patch conv)."""
+    import ctypes
+    lib = _lib.load()
+    _req(imgs, torch.float32, "imgs"); _req(out, torch.bfloat16, "out")
+    assert imgs.is_contiguous() and out.is_contiguous()
+    N, _, H, W = imgs.shape
+    assert out.shape[0] == N * (H // 14) * (W // 14)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    rc = lib.pi3b_patch_pack(_stream(), imgs.data_ptr(), out.data_ptr(), N, H, W, out.shape[1],
+                             ctypes.cast(m3, ctypes.c_void_p), ctypes.cast(s3, ctypes.c_void_p))
+    _lib.check(rc, "pi3b_patch_pack")
+    return out
+
+
+def broadcast_rows(table: torch.Tensor, out: torch.Tensor, num_groups: int) -> torch.Tensor:
+    lib = _lib.load()
+    _req(table, torch.float32, "table"); _req(out, torch.float32, "out")
+    assert table.is_contiguous() and out.is_contiguous() and out.shape[0] == num_groups * table.shape[0]
+    rc = lib.pi3b_broadcast_rows(_stream(), table.data_ptr(), out.data_ptr(), num_groups, table.shape[0], table.shape[1])
+    _lib.check(rc, "pi3b_broadcast_rows")
+    return out
+
+
+def cast_bf16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, torch.float32, "x"); _req(out, torch.bfloat16, "out")
+    assert x.shape == out.shape and x.stride(1) == 1 and out.stride(1) == 1
+    rc = lib.pi3b_cast_f32_bf16(_stream(), x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1])
+    _lib.check(rc, "pi3b_cast_f32_bf16")
+    return out
+
+
+def unpatchify_points_conf(feat_pts, feat_conf, poses, local_points, points, conf, N, H, W, tokens_per_frame,
+                           n_special) -> None:
+    lib = _lib.load()
+    for t, nm in ((feat_pts, "feat_pts"), (feat_conf, "feat_conf"), (poses, "poses"), (local_points, "local_points"),
+                  (points, "points"), (conf, "conf")):
+        _req(t, torch.float32, nm)
+    assert poses.is_contiguous() and local_points.is_contiguous() and points.is_contiguous() and conf.is_contiguous()
+    rc = lib.pi3b_unpatchify_points_conf(_stream(), feat_pts.data_ptr(), feat_pts.stride(0), feat_conf.data_ptr(),
+                                         feat_conf.stride(0), poses.data_ptr(), local_points.data_ptr(),
+                                         points.data_ptr(), conf.data_ptr(), N, H, W, tokens_per_frame, n_special)
+    _lib.check(rc, "pi3b_unpatchify_points_conf")
+
+
+def meanpool_tokens(x: torch.Tensor, out: torch.Tensor, N: int, tokens_per_frame: int, n_special: int) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, torch.float32, "x"); _req(out, torch.float32, "out")
+    assert x.stride(1) == 1 and out.is_contiguous() and out.shape == (N, x.shape[1])
+    rc = lib.pi3b_meanpool_tokens(_stream(), x.data_ptr(), x.stride(0), out.data_ptr(), N, x.shape[1], tokens_per_frame,
+                                  n_special)
+    _lib.check(rc, "pi3b_meanpool_tokens")
+    return out
+
+
+def pose_from_9d(rot9: torch.Tensor, trans: torch.Tensor, poses: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _req(rot9, torch.float32, "rot9"); _req(trans, torch.float32, "trans"); _req(poses, torch.float32, "poses")
+    assert poses.is_contiguous() and rot9.stride(1) == 1 and trans.stride(1) == 1
+    rc = lib.pi3b_pose_from_9d(_stream(), rot9.data_ptr(), rot9.stride(0), trans.data_ptr(), trans.stride(0),
+                               poses.data_ptr(), rot9.shape[0])
+    _lib.check(rc, "pi3b_pose_from_9d")
+    return poses
+
+
+def mask_depth_edge(local_points: torch.Tensor, conf: torch.Tensor, mask: torch.Tensor, conf_thr: float = 0.1,
+                    rtol: float = 0.03) -> torch.Tensor:
+    """mask (N,H,W) uint8 = sigmoid(conf) > conf_thr and not depth_edge(z, rtol); z = local_points[..., 2]."""
+    lib = _lib.load()
+    _req(local_points, torch.float32, "local_points"); _req(conf, torch.float32, "conf")
+    assert local_points.is_contiguous() and conf.is_contiguous() and mask.is_contiguous() and mask.dtype == torch.uint8
+    N, H, W = local_points.shape[:3]
+    rc = lib.pi3b_mask_depth_edge(_stream(), local_points.data_ptr() + 8, 3, conf.data_ptr(), mask.data_ptr(), N, H, W,
+                                  conf_thr, rtol)
+    _lib.check(rc, "pi3b_mask_depth_edge")
+    return mask
+
+
+def keypoint_gather(points, local_points, conf, mask, images, keypoints):
+    """Sample dense maps at keypoints (N,K,2) (x, y): bilinear points / local_points / colours (uint8),
+    nearest conf / mask. Returns (points (N,K,3) f32, local (N,K,3) f32, conf (N,K,1) f32, mask (N,K,1) bool,
+    colors (N,K,3) uint8 or None)."""
+    lib = _lib.load()
+    for t, nm in ((points, "points"), (local_points, "local_points"), (conf, "conf"), (keypoints, "keypoints")):
+        _req(t, torch.float32, nm)
+        assert t.is_contiguous()
+    assert mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous()
+    N, H, W = points.shape[:3]
+    K = keypoints.shape[1]
+    dev = points.device
+    o_p = torch.empty(N, K, 3, device=dev); o_l = torch.empty(N, K, 3, device=dev)
+    o_c = torch.empty(N, K, 1, device=dev); o_m = torch.empty(N, K, 1, device=dev, dtype=torch.uint8)
+    o_col = None
+    if images is not None:
+        _req(images, torch.float32, "images")
+        assert images.is_contiguous() and images.shape == (N, 3, H, W)
+        o_col = torch.empty(N, K, 3, device=dev, dtype=torch.uint8)
+    rc = lib.pi3b_keypoint_gather(_stream(), points.data_ptr(), local_points.data_ptr(), conf.data_ptr(),
+                                  mask.data_ptr(), _ptr(images), keypoints.data_ptr(), o_p.data_ptr(), o_l.data_ptr(),
+                                  o_c.data_ptr(), o_m.data_ptr(), _ptr(o_col), N, K, H, W)
+    _lib.check(rc, "pi3b_keypoint_gather")
+    return o_p, o_l, o_c, o_m.bool(), o_col
+
+
+def sample_grid(local_points, conf, ys, xs, conf_thr: float = 0.1):
+    """Nearest-downsampled local points [N, hs*ws, 3] and validity (sigmoid(conf) > thr) [N, hs*ws] uint8."""
+    lib = _lib.load()
+    _req(local_points, torch.float32, "local_points"); _req(conf, torch.float32, "conf")
+    assert ys.dtype == torch.int32 and xs.dtype == torch.int32 and ys.is_cuda and xs.is_cuda
+    N, H, W = local_points.shape[:3]
+    hs, ws = ys.numel(), xs.numel()
+    pts = torch.empty(N, hs * ws, 3, device=local_points.device)
+    val = torch.empty(N, hs * ws, device=local_points.device, dtype=torch.uint8)
+    rc = lib.pi3b_sample_grid(_stream(), local_points.data_ptr(), conf.data_ptr(), ys.data_ptr(), xs.data_ptr(),
+                              pts.data_ptr(), val.data_ptr(), N, H, W, hs, ws, conf_thr)
+    _lib.check(rc, "pi3b_sample_grid")
+    return pts, val
+
+
+def median_ratio(a: torch.Tensor, b: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Lower median of a/b over mask (1-D strided views allowed). Returns a 2-vector (median, count) on device."""
+    lib = _lib.load()
+    _req(a, torch.float32, "a"); _req(b, torch.float32, "b")
+    assert a.dim() == 1 and b.dim() == 1 and mask.dim() == 1 and mask.dtype == torch.uint8 and mask.is_contiguous()
+    out = torch.empty(2, device=a.device)
+    rc = lib.pi3b_median_ratio(_stream(), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), mask.data_ptr(),
+                               a.numel(), out.data_ptr())
+    _lib.check(rc, "pi3b_median_ratio")
+    return out
+
+
+def umeyama_sim3(qry: torch.Tensor, ref: torch.Tensor, valid: Optional[torch.Tensor] = None):
+    """Batched closed-form similarity mapping qry -> ref. qry, ref: (B, n, 3) fp32; valid (B, n) uint8 or None.
+    Returns (T (B,4,4) = [sR|t], scale (B,), count (B,))."""
+    lib = _lib.load()
+    _req(qry, torch.float32, "qry"); _req(ref, torch.float32, "ref")
+    assert qry.shape == ref.shape and qry.dim() == 3 and qry.is_contiguous() and ref.is_contiguous()
+    if valid is not None:
+        assert valid.dtype == torch.uint8 and valid.is_contiguous() and valid.shape == qry.shape[:2]
+    out = torch.empty(qry.shape[0], 18, device=qry.device)
+    rc = lib.pi3b_umeyama_sim3_batched(_stream(), qry.data_ptr(), ref.data_ptr(), _ptr(valid), qry.shape[0],
+                                       qry.shape[1], out.data_ptr())
+    _lib.check(rc, "pi3b_umeyama_sim3_batched")
+    return out[:, :16].reshape(-1, 4, 4), out[:, 16], out[:, 17]
