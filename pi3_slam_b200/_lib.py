@@ -87,7 +87,12 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     return lib
 
 
+launch_count = 0   # number of C-ABI kernel launches issued by this process (bench.py reports it)
+
+
 def check(rc: int, what: str) -> None:
+    global launch_count
+    launch_count += 1
     if rc != 0:
         msg = load().pi3b_last_error()
         raise Pi3bError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

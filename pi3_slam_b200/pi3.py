@@ -71,6 +71,9 @@ class Pi3(nn.Module):
         self._packed: Optional[dict] = None       # bf16 / padded operands, built lazily on the device
         self._shape_cache: Dict[Tuple[int, int], dict] = {}
         self._arena: Dict[tuple, dict] = {}
+        # when set to a list, (start, end) CUDA events of every chunk-global attention launch are appended
+        # (bench.py uses them for the live roofline of the dominant kernel)
+        self.global_attn_events: Optional[list] = None
 
     # ------------------------------------------------------------------ loading
     @classmethod
@@ -244,7 +247,14 @@ class Pi3(nn.Module):
         ops.gemm(h, b["qkv_w"], qkv, bias=b["qkv_b"])
         if rope or b["qn"] is not None:
             ops.qknorm_rope(qkv, HEADS, T, N_SPECIAL, pw, cs if rope else None, b["qn"], b["kn"], 1e-5)
-        ops.attention_qkv(qkv, att, num_seqs, seq_len, HEADS, 0.125)
+        if self.global_attn_events is not None and seq_len != T:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.attention_qkv(qkv, att, num_seqs, seq_len, HEADS, 0.125)
+            e1.record()
+            self.global_attn_events.append((e0, e1))
+        else:
+            ops.attention_qkv(qkv, att, num_seqs, seq_len, HEADS, 0.125)
         ops.gemm(att, b["proj_w"], x, bias=b["proj_b"], gamma=b["ls1"], resid=x)
         ops.layernorm(x, b["n2"][0], b["n2"][1], 1e-6, h)
         ops.gemm(h, b["fc1_w"], mlp, bias=b["fc1_b"], act=ops.ACT_GELU)
