@@ -137,8 +137,8 @@ class OfflineChunkCreator:
             dt_inf = max(1e-6, time.time() - t0)
             fps = num_frames / dt_inf if num_frames > 0 else 0.0
             print(f"   ⏱️ Inference: {dt_inf:.3f}s for {num_frames} frames  ->  {fps:.2f} FPS")
-            _metrics = {"infer_s": float(dt_inf), "num_frames": int(num_frames), "fps": float(fps),
-                        "device_s": float(ev0.elapsed_time(ev1) * 1e-3)}
+            _metrics = {"infer_s": float(dt_inf), "num_frames": int(num_frames), "fps": float(fps)}
+            self.last_device_seconds = float(ev0.elapsed_time(ev1) * 1e-3)
 
             masks = self._compute_masks(pi3_result)[0]
 
@@ -205,6 +205,19 @@ class OfflineChunkCreator:
                 result["intrinsics"] = result["camera_params"].get("intrinsics", None)
         return result
 
+    @staticmethod
+    def _gather_manifest(manifest: List[Dict]) -> List[Dict]:
+        """The only collective on this path: every rank contributes its (small) manifest entries; the merged
+        list, ordered by chunk index, is what rank 0 writes to chunks_manifest.json."""
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return manifest
+        world = torch.distributed.get_world_size()
+        if world == 1:
+            return manifest
+        gathered: List = [None] * world
+        torch.distributed.all_gather_object(gathered, manifest)
+        return sorted((e for part in gathered for e in part), key=lambda e: e["chunk_index"])
+
     # ------------------------------------------------------------------ whole sequence
     def process_and_save(self, image_paths: Sequence, loader: Optional[Callable] = None,
                          target_size: Optional[Tuple[int, int]] = None) -> List[str]:
@@ -270,11 +283,7 @@ class OfflineChunkCreator:
             print(f"   Steady-state FPS (full {self.config.chunk_length}-frame chunks, median): "
                   f"{steady[len(steady) // 2]:.2f} FPS")
 
-        # the only collective on this path: small manifest entries to rank 0
-        if world > 1:
-            gathered: List = [None] * world
-            torch.distributed.all_gather_object(gathered, manifest)
-            manifest = sorted((e for part in gathered for e in part), key=lambda e: e["chunk_index"])
+        manifest = self._gather_manifest(manifest)
         if rank == 0:
             try:
                 with open(os.path.join(self.config.output_dir, "chunks_manifest.json"), "w") as f:

@@ -1,0 +1,195 @@
+"""GPU: OfflineChunkCreator drop-in contract and parity against the reference's own chunk output
+(tests/golden/chunk_tiny.pt, produced by the real reference `_process_single_chunk` on CPU)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def model():
+    from pi3_slam_b200.pi3 import Pi3
+    from pi3_slam_b200.synthetic import make_state_dict
+    m = Pi3()
+    m.load_state_dict(make_state_dict(0), strict=True)
+    return m.to("cuda").eval()
+
+
+def _creator(model, out_dir, **kw):
+    from pi3_slam_b200.offline_chunk_creator import OfflineChunkCreator, OfflineCreatorConfig
+    cfg = OfflineCreatorConfig(model_path="unused", output_dir=str(out_dir), device="cuda", do_metric_depth=False,
+                               keypoint_type="grid", **kw)
+    return OfflineChunkCreator(cfg, model=model)
+
+
+def test_single_chunk_matches_reference_golden(model, tmp_path):
+    from oracle.pi3_oracle import pose_errors, rel_l2
+    from pi3_slam_b200.host.keypoints import GridKeypointExtractor
+    from pi3_slam_b200.synthetic import make_frames
+
+    g = torch.load(os.path.join(GOLDEN, "chunk_tiny.pt"), weights_only=False)
+    gold, N, H, W = g["chunk"], g["N"], g["H"], g["W"]
+    creator = _creator(model, tmp_path, max_num_keypoints=g["max_kp"])
+    # the golden was drawn from the CPU generator (reference run with device='cpu'); same stream here
+    creator.keypoint_extractor = GridKeypointExtractor(g["max_kp"], device="cpu")
+    creator.target_size = (H, W)
+    paths = [(f"frame_{i:04d}.png",) for i in range(N)]
+    torch.manual_seed(g["seed"])
+    out = creator._process_single_chunk(make_frames(N, H, W)[None], paths)
+
+    assert set(out.keys()) == set(gold.keys())
+    for k, v in gold.items():
+        if torch.is_tensor(v):
+            assert out[k].shape == v.shape and out[k].dtype == v.dtype and not out[k].is_cuda, k
+    # bit-exact: keypoints and bookkeeping
+    for k in ("keypoints", "descriptors", "scores"):
+        assert torch.equal(out[k], gold[k]), k
+    assert out["image_paths"] == gold["image_paths"]
+    assert out["original_width"] == W and out["original_height"] == H
+    assert set(out["_metrics"]) == {"infer_s", "num_frames", "fps"} and out["_metrics"]["num_frames"] == N
+    assert set(out["camera_params"]) == set(gold["camera_params"])
+    # colours come from the input frames only: exact up to the uint8 truncation of a 1-ulp different product
+    dcol = (out["colors"].float() - gold["colors"].float()).abs()
+    assert dcol.max() <= 1 and (dcol > 0).float().mean() < 0.02
+    # geometry within the bf16 tolerance of the forward
+    assert rel_l2(out["points"].float(), gold["points"].float()) < 1e-2
+    assert rel_l2(out["local_points"].float(), gold["local_points"].float()) < 1e-2
+    assert rel_l2(out["conf"].float(), gold["conf"].float()) < 2e-2
+    rot, rel_t = pose_errors(out["camera_poses"], gold["camera_poses"])
+    assert rot < 1e-3 and rel_t < 1e-3
+    agree = (out["masks"] == gold["masks"]).float().mean().item()
+    print(f"mask agreement {agree:.4f}")
+    assert agree >= 0.97          # pixels whose depth-edge ratio sits within bf16 noise of the 0.03 threshold
+    for k in ("focal", "fx", "fy"):
+        assert torch.allclose(out["camera_params"][k], gold["camera_params"][k], rtol=2e-2), k
+    assert torch.equal(out["camera_params"]["cx"], gold["camera_params"]["cx"])
+    assert torch.equal(out["camera_params"]["cy"], gold["camera_params"]["cy"])
+    assert torch.equal(out["intrinsics"], out["camera_params"]["intrinsics"])
+
+
+def test_device_postprocessing_matches_oracle_on_same_dense_maps(model):
+    """Masks / keypoint sampling / colours / intrinsics on the device vs the chunk oracle, both fed the SAME
+    dense maps (so the comparison is exact and independent of the forward's bf16 noise)."""
+    from oracle import chunk_oracle as co
+    from pi3_slam_b200 import ops
+    from pi3_slam_b200.host.camera_estimation import estimate_camera_parameters_single_chunk
+    g = torch.load(os.path.join(GOLDEN, "chunk_tiny.pt"), weights_only=False)
+    d, N, H, W = g["dense"], g["N"], g["H"], g["W"]
+    lp, pts, conf = d["local_points"].cuda(), d["points"].cuda(), d["conf"].cuda()
+    mask = torch.empty(N, H, W, device="cuda", dtype=torch.uint8)
+    ops.mask_depth_edge(lp, conf, mask)
+    ref_mask = co.compute_masks(d["local_points"], d["conf"])
+    assert torch.equal(mask.bool().cpu(), ref_mask)
+    torch.manual_seed(7)
+    kps = co.grid_keypoints(N, H, W, 40)
+    from pi3_slam_b200.synthetic import make_frames
+    imgs = make_frames(N, H, W)
+    p, l, c, m, col = ops.keypoint_gather(pts, lp, conf, mask, imgs.cuda(), kps.cuda())
+    ref = co.interpolate_at_keypoints(d["points"], d["local_points"], d["conf"], ref_mask, kps, H, W)
+    assert torch.allclose(p.cpu(), ref["points"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(l.cpu(), ref["local_points"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(c.cpu(), ref["conf"]) and torch.equal(m.cpu(), ref["masks"])
+    dcol = (col.cpu().int() - co.colors_at_keypoints(imgs, kps).int()).abs()
+    assert dcol.max() <= 1 and (dcol > 0).float().mean() < 0.02
+    cp = estimate_camera_parameters_single_chunk(lp, conf)
+    for k, v in g["chunk"]["camera_params"].items():
+        assert cp[k].shape == v.shape and torch.allclose(cp[k].cpu(), v, rtol=1e-4, atol=1e-6), k
+    # median ratio == torch lower median
+    a = torch.rand(5000, device="cuda") + 0.5
+    b = torch.rand(5000, device="cuda") + 0.5
+    mk = (torch.rand(5000, device="cuda") > 0.3)
+    got = ops.median_ratio(a, b, mk.to(torch.uint8))
+    assert got[0].item() == (a[mk] / b[mk]).median().item() and int(got[1].item()) == int(mk.sum())
+
+
+def test_process_and_save_contract(model, tmp_path):
+    from pi3_slam_b200.synthetic import make_frames
+    creator = _creator(model, tmp_path, chunk_length=4, overlap=1, max_num_keypoints=25, keypoint_seed=11)
+    H, W = 56, 84
+    paths = [f"/data/seq/frame_{i:04d}.png" for i in range(9)]
+    index = {p: i for i, p in enumerate(paths)}
+    files = creator.process_and_save(paths, loader=lambda ps, ts: torch.cat([make_frames(1, *ts, start_index=index[p]) for p in ps]),
+                                     target_size=(H, W))
+    assert [os.path.basename(f) for f in files] == ["chunk_000000.pt", "chunk_000001.pt", "chunk_000002.pt"]
+    manifest = json.load(open(tmp_path / "chunks_manifest.json"))
+    meta = json.load(open(tmp_path / "chunk_metadata.json"))
+    assert meta == {"chunk_length": 4, "overlap": 1, "target_size": [H, W]}
+    assert [(m["start_idx"], m["end_idx"], m["num_frames"]) for m in manifest] == [(0, 4, 4), (3, 7, 4), (6, 9, 3)]
+    assert manifest[1]["image_paths"] == [[p] for p in paths[3:7]] and manifest[1]["file"] == "chunk_000001.pt"
+    c = torch.load(files[2], weights_only=False)
+    assert c["chunk_index"] == 2 and c["start_idx"] == 6 and c["end_idx"] == 9
+    assert c["points"].shape == (3, 25, 3) and c["points"].dtype == torch.float16
+    assert c["image_paths"] == [(p,) for p in paths[6:9]]
+    # overlap frame 3 is the last frame of chunk 0 and the first of chunk 1; re-running the sequence
+    # reproduces the files bit for bit (per-chunk keypoint seeding => independent of processing order)
+    first = torch.load(files[1], weights_only=False)
+    creator2 = _creator(model, tmp_path / "again", chunk_length=4, overlap=1, max_num_keypoints=25, keypoint_seed=11)
+    files2 = creator2.process_and_save(paths, loader=lambda ps, ts: torch.cat([make_frames(1, *ts, start_index=index[p]) for p in ps]),
+                                       target_size=(H, W))
+    again = torch.load(files2[1], weights_only=False)
+    for k in ("points", "local_points", "conf", "masks", "camera_poses", "keypoints", "colors", "intrinsics"):
+        assert torch.equal(first[k], again[k]), k
+
+
+def test_umeyama_kernel_and_chunk_alignment():
+    from oracle import chunk_oracle as co
+    from pi3_slam_b200 import ops
+    from pi3_slam_b200.alignment import align_consecutive_chunks
+    rng = np.random.default_rng(3)
+    # batched known-answer + padding/valid handling
+    Pn, n = 5, 300
+    q = rng.normal(size=(Pn, n, 3)).astype(np.float32) * 3
+    Ts = []
+    r = np.zeros_like(q)
+    valid = np.ones((Pn, n), dtype=np.uint8)
+    for i in range(Pn):
+        U, _, Vt = np.linalg.svd(rng.normal(size=(3, 3)))
+        R = U @ np.diag([1, 1, np.linalg.det(U @ Vt)]) @ Vt
+        s, t = float(rng.uniform(0.5, 2.0)), rng.normal(size=3)
+        r[i] = (s * q[i] @ R.T + t).astype(np.float32)
+        valid[i, n - 20 * i:] = 0
+        r[i, n - 20 * i:] = 1e6          # garbage in the padded tail must be ignored
+        Ts.append(co.sim3_matrix(s, R, t))
+    T, scale, count = ops.umeyama_sim3(torch.from_numpy(q).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(valid).cuda())
+    assert np.abs(T.cpu().numpy() - np.stack(Ts)).max() < 2e-4
+    assert count.cpu().tolist() == [float(n - 20 * i) for i in range(Pn)]
+    # noisy correspondences: kernel == float64 numpy oracle
+    rn = r + rng.normal(size=r.shape).astype(np.float32) * 0.05
+    T2, _, _ = ops.umeyama_sim3(torch.from_numpy(q).cuda(), torch.from_numpy(rn).cuda(), torch.from_numpy(valid).cuda())
+    for i in range(Pn):
+        k = n - 20 * i
+        ref = co.sim3_matrix(*co.umeyama_sim3(q[i, :k], rn[i, :k]))
+        assert np.abs(T2[i].cpu().numpy() - ref).max() < 2e-4
+    # chunk-level: three synthetic chunks that are Sim3 images of one world (per-(frame, lattice cell) points)
+    L, ov, K = 6, 2, 50
+    lattice = np.stack(np.meshgrid(np.arange(10), np.arange(6)), -1).reshape(-1, 2).astype(np.float32) * 8 + 4.25
+    cell_id = {(float(x), float(y)): i for i, (x, y) in enumerate(lattice)}
+    cell_world = {f: rng.normal(size=(len(lattice), 3)).astype(np.float32) * 2 + np.array([0, 0, 6], dtype=np.float32)
+                  for f in range(20)}
+    dicts, gts = [], []
+    for ci in range(3):
+        U, _, Vt = np.linalg.svd(rng.normal(size=(3, 3)))
+        R = U @ np.diag([1, 1, np.linalg.det(U @ Vt)]) @ Vt
+        gts.append(co.sim3_matrix(float(rng.uniform(0.7, 1.4)), R, rng.normal(size=3)))      # chunk frame -> world
+        Tinv = np.linalg.inv(gts[-1])
+        frames = range(ci * (L - ov), ci * (L - ov) + L)
+        kp = np.stack([lattice[rng.permutation(len(lattice))[:K]] for _ in frames])      # a random subset per frame
+        pts = np.zeros((L, K, 3), dtype=np.float32)
+        for a, f in enumerate(frames):
+            ids = [cell_id[(float(x), float(y))] for x, y in kp[a]]
+            pts[a] = (np.c_[cell_world[f][ids], np.ones(K)] @ Tinv.T)[:, :3]
+        poses = np.tile(np.eye(4, dtype=np.float32), (L, 1, 1))
+        dicts.append({"points": torch.from_numpy(pts).half(), "keypoints": torch.from_numpy(kp).half(),
+                      "masks": torch.ones(L, K, 1, dtype=torch.bool), "camera_poses": torch.from_numpy(poses)})
+    res = align_consecutive_chunks(dicts, L, ov)
+    for k in range(2):
+        ref = co.chunk_pair_alignment(dicts[k], dicts[k + 1], L, ov)
+        assert np.abs(res["pairwise"][k].numpy() - ref).max() < 5e-3
+        expect = np.linalg.inv(gts[k]) @ gts[k + 1]              # qry frame -> ref frame
+        assert np.abs(res["pairwise"][k].numpy() - expect).max() < 3e-2    # fp16 storage of the points
+    assert res["cumulative"].shape == (3, 4, 4)
