@@ -9,7 +9,10 @@ import ctypes
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libpi3b200.so"
+import os as _os
+
+# PI3B_LIB lets kernel experiments point at an alternative build of the same ABI (never a different backend)
+_LIB_PATH = Path(_os.environ.get("PI3B_LIB", Path(__file__).resolve().parent / "libpi3b200.so"))
 _lib = None
 
 # name -> (restype, argtypes); mirrors include/pi3b200.h one to one.

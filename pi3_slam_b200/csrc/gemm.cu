@@ -97,57 +97,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===== TMA producer: the whole warp walks the tile schedule, one elected lane issues (operands stay uniform) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
           mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           // activations stream through once; the (small) weight panel is reused by every m block
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * kBlockM, kEvictNormal);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, kEvictLast);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TF32 ? 2u : 1u, kBlockM, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit =====
+    constexpr uint32_t idesc = make_idesc(TF32 ? 2u : 1u, kBlockM, BLOCK_N, 0, 0);
+    const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+    const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem + S::A_BYTES), 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + S::A_BYTES;
+        const uint64_t soff = uint64_t((stage * S::STAGE_BYTES) >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             if (TF32)
-              umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+              umma_tf32_ss(d_tmem, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (kb | k) != 0);
             else
-              umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+              umma_f16_ss(d_tmem, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ===== epilogue warps: TMEM -> registers -> fused epilogue -> HBM =====

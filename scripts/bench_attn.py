@@ -4,7 +4,7 @@ from bench_kernels import time_cuda
 
 
 def bench_attn(results):
-    for (B, S, H, iters) in [(100, 1004, 16, 5), (100, 643, 16, 5), (1, 20080, 16, 3), (1, 64300, 16, 2), (1, 100400, 16, 2)]:
+    for (B, S, H, iters) in [(100, 1004, 16, 5), (100, 643, 16, 5), (1, 20080, 16, 3), (1, 64300, 16, 4), (1, 100400, 16, 4)]:
         qkv = torch.randn(B * S, 3 * H * 64, device="cuda").bfloat16()
         out = torch.empty(B * S, H * 64, device="cuda", dtype=torch.bfloat16)
         t = time_cuda(lambda: ops.attention_qkv(qkv, out, B, S, H), iters=iters, warmup=1)
