@@ -152,6 +152,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level
+        os.environ["NCCL_DEBUG"] = os.environ.get("PI3B_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
 
     sd = make_state_dict(0)
@@ -223,11 +225,13 @@ def main():
         attn_flops = 16 * 4.0 * (frames * T) ** 2 * 64          # one chunk-global attention launch
         attn_avg_ms = sum(attn_ms) / max(1, len(attn_ms))
         achieved = attn_flops / (attn_avg_ms * 1e-3) / 1e12 if attn_ms else None
-        traffic = None
+        traffic, traffic_detail = None, None
         tpath = os.path.join(ROOT, "profiles", "attn_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(args.workload)
+                traffic_detail = json.load(f).get(args.workload)
+            if traffic_detail:
+                traffic = traffic_detail["bytes_per_launch"]   # dram read + write of one ncu --set full capture
         line = {
             "metric": "pi3_chunk_frames_per_sec", "value": world * frames / (ms_step * 1e-3), "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -238,9 +242,10 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "model_tflops_per_step": fl["total"] / 1e12,
-            "achieved_tflops": fl["total"] / (ms_step * 1e-3) / 1e12,
+            "achieved_tflops": world * fl["total"] / (ms_step * 1e-3) / 1e12,
             "frac_of_bf16_peak": {"burst": fl["total"] / (ms_step * 1e-3) / 1e12 / peaks["burst"],
-                                  "sustained": fl["total"] / (ms_step * 1e-3) / 1e12 / peaks["sustained"]},
+                                  "sustained": fl["total"] / (ms_step * 1e-3) / 1e12 / peaks["sustained"],
+                                  "note": "per-GPU achieved / per-GPU measured peak"},
             "roofline": {"kernel": "attn_fwd_kernel (chunk-global attention, 18 launches/step)", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["sustained"]) if achieved else None,
@@ -248,7 +253,7 @@ def main():
                          "peak_source": f"{peaks['source']} (sustained figure: kernel timed inside a long step)",
                          "flops_per_launch": attn_flops, "avg_launch_ms": attn_avg_ms, "launches_timed": len(attn_ms),
                          "share_of_step": (sum(attn_ms) / args.steps) / ms_step if attn_ms else None,
-                         "traffic": traffic},
+                         "traffic": traffic, "traffic_detail": traffic_detail},
         }
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(CPU_SAMPLE_FRAMES, H, W, 1, 0, sd)

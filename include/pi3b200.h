@@ -38,13 +38,14 @@ int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda, const void
               const float* bias, const float* gamma, const float* resid, int64_t ld_resid, void* out, int64_t ldo,
               int out_f32, int act, int grp_in, int grp_out, int grp_off);
 
-/* out = softmax(q k^T * scale) v, head_dim 64, bf16, per (sequence, head). Rows of sequence s are
- * [s*seq_len, (s+1)*seq_len); head h lives at columns {q,k,v}_col0 + 64*h of its operand; out at column 64*h.
+/* out = softmax(q k^T * scale) v, head_dim 64, bf16, per (sequence, head). Sequence s owns query / output rows
+ * [s*q_len, (s+1)*q_len) and key / value rows [s*kv_len, (s+1)*kv_len) (q_len != kv_len: the sequence-parallel case,
+ * local queries against all-gathered K/V); head h lives at columns {q,k,v}_col0 + 64*h of its operand; out at 64*h.
  * replaces: F.scaled_dot_product_attention at pi3/models/layers/attention.py:102-104 and :336-338
  *   (frame-local and chunk-global attention of pi3/models/pi3.py:156-166). */
 int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
                        int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo, int num_seqs,
-                       int seq_len, int num_heads, float scale);
+                       int q_len, int kv_len, int num_heads, float scale);
 
 /* out[M,1024] = LayerNorm(x[M,1024]) * gamma + beta (fp32 in; bf16 or fp32 out; in place allowed).
  * If override_rows != NULL, rows r with r % period < n_override are set to override_rows[r % period] instead.

@@ -23,9 +23,9 @@ SIGNATURES = {
     # stream, in_dtype, A, lda, W, ldw, M, N, K, bias, gamma, resid, ld_resid, out, ldo, out_f32, act, grp_in, grp_out, grp_off
     "pi3b_gemm": (c_int, [_P, c_int, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, _P,
                           c_int64, c_int, c_int, c_int, c_int, c_int]),
-    # stream, q, k, v, ldq, ldk, ldv, q_col0, k_col0, v_col0, out, ldo, num_seqs, seq_len, num_heads, scale
+    # stream, q, k, v, ldq, ldk, ldv, q_col0, k_col0, v_col0, out, ldo, num_seqs, q_len, kv_len, num_heads, scale
     "pi3b_attn_fwd_hd64": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64,
-                                   c_int, c_int, c_int, c_float]),
+                                   c_int, c_int, c_int, c_int, c_float]),
     # stream, x, ldx, gamma, beta, eps, out, ldo, out_f32, M, D, override_rows, period, n_override
     "pi3b_layernorm": (c_int, [_P, _P, c_int64, _P, _P, c_float, _P, c_int64, c_int, c_int, c_int, _P, c_int, c_int]),
     # stream, qkv, ld, M, heads, tokens_per_frame, n_special, patch_w, qn_w, qn_b, kn_w, kn_b, eps, cs_table, table_rows, do_rope

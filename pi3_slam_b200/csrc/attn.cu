@@ -45,7 +45,7 @@ struct AttnSmem {
 };
 
 struct AttnParams {
-  int num_seqs, seq_len, num_heads;
+  int num_seqs, q_len, kv_len, num_heads;  // per sequence: q_len query rows attend to kv_len key/value rows
   int q_col0, k_col0, v_col0;  // element column of head 0 inside each operand's rows
   __nv_bfloat16* out;
   int ldo;
@@ -118,17 +118,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int lane = threadIdx.x & 31;
 
   // work item: query-pair fastest, then sequence, then head (neighbouring CTAs share one head's K/V in L2)
-  const int num_qpairs = (p.seq_len + 255) / 256;
+  const int num_qpairs = (p.q_len + 255) / 256;
   int item = blockIdx.x;
   const int qp = item % num_qpairs;
   item /= num_qpairs;
   const int seq = item % p.num_seqs;
   const int head = item / p.num_seqs;
-  const int row_base = seq * p.seq_len;          // first row of this sequence in the operand matrices
+  const int row_base = seq * p.q_len;            // first query / output row of this sequence
+  const int kv_base = seq * p.kv_len;            // first key / value row of this sequence
   const int q0 = qp * 256;                       // first query row (within the sequence) of this CTA
-  const int q_valid = min(256, p.seq_len - q0);  // valid query rows in this CTA
+  const int q_valid = min(256, p.q_len - q0);    // valid query rows in this CTA
   const int num_t = q_valid > 128 ? 2 : 1;       // second Q tile entirely past the end -> skip it
-  const int num_kv = (p.seq_len + 127) / 128;
+  const int num_kv = (p.kv_len + 127) / 128;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -178,10 +179,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (elect_one()) {
           mbar_expect_tx(&k_full[s], kTileBytes);
           tma_load_2d(smem + AttnSmem::K_OFF + s * kTileBytes, &tmK, &k_full[s], p.k_col0 + head * 64,
-                      row_base + j * 128, kEvictLast);
+                      kv_base + j * 128, kEvictLast);
           mbar_expect_tx(&v_full[s], kTileBytes);
           tma_load_2d(smem + AttnSmem::V_OFF + s * kTileBytes, &tmV, &v_full[s], p.v_col0 + head * 64,
-                      row_base + j * 128, kEvictLast);
+                      kv_base + j * 128, kEvictLast);
         }
         __syncwarp();
       }
@@ -272,7 +273,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[t]);
 
-        const int kv_valid = p.seq_len - j * 128;
+        const int kv_valid = p.kv_len - j * 128;
         if (kv_valid < 128) {
 #pragma unroll
           for (int c = 0; c < 128; ++c)
@@ -380,23 +381,24 @@ using namespace pi3b;
 
 extern "C" int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
                                   int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo,
-                                  int num_seqs, int seq_len, int num_heads, float scale) {
+                                  int num_seqs, int q_len, int kv_len, int num_heads, float scale) {
   PI3B_REQUIRE(q && k && v && out, "pi3b_attn_fwd_hd64: null pointer");
-  PI3B_REQUIRE(num_seqs > 0 && seq_len > 0 && num_heads > 0, "pi3b_attn_fwd_hd64: bad shape");
+  PI3B_REQUIRE(num_seqs > 0 && q_len > 0 && kv_len > 0 && num_heads > 0, "pi3b_attn_fwd_hd64: bad shape");
   PI3B_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
                "pi3b_attn_fwd_hd64: row pitches must be multiples of 8 elements");
   PI3B_REQUIRE(q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0, "pi3b_attn_fwd_hd64: column offsets %% 8");
   PI3B_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "pi3b_attn_fwd_hd64: out must be 16-byte aligned");
-  const uint64_t rows = uint64_t(num_seqs) * seq_len;
-  PI3B_REQUIRE(rows < (1ull << 31), "pi3b_attn_fwd_hd64: too many rows");
-  const int64_t items = int64_t((seq_len + 255) / 256) * num_seqs * num_heads;
+  const uint64_t rows = uint64_t(num_seqs) * q_len;
+  const uint64_t kv_rows = uint64_t(num_seqs) * kv_len;
+  PI3B_REQUIRE(rows < (1ull << 31) && kv_rows < (1ull << 31), "pi3b_attn_fwd_hd64: too many rows");
+  const int64_t items = int64_t((q_len + 255) / 256) * num_seqs * num_heads;
   PI3B_REQUIRE(items < (1ll << 31), "pi3b_attn_fwd_hd64: too many work items");
 
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   if ((rc = make_tmap_2d(&tmQ, q, 0, rows, uint64_t(q_col0) + 64ull * num_heads, uint64_t(ldq) * 2, 128, 64))) return rc;
-  if ((rc = make_tmap_2d(&tmK, k, 0, rows, uint64_t(k_col0) + 64ull * num_heads, uint64_t(ldk) * 2, 128, 64))) return rc;
-  if ((rc = make_tmap_2d(&tmV, v, 0, rows, uint64_t(v_col0) + 64ull * num_heads, uint64_t(ldv) * 2, 128, 64))) return rc;
+  if ((rc = make_tmap_2d(&tmK, k, 0, kv_rows, uint64_t(k_col0) + 64ull * num_heads, uint64_t(ldk) * 2, 128, 64))) return rc;
+  if ((rc = make_tmap_2d(&tmV, v, 0, kv_rows, uint64_t(v_col0) + 64ull * num_heads, uint64_t(ldv) * 2, 128, 64))) return rc;
 
   static bool configured = false;
   if (!configured) {
@@ -406,7 +408,7 @@ extern "C" int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, co
     configured = true;
   }
   AttnParams p;
-  p.num_seqs = num_seqs; p.seq_len = seq_len; p.num_heads = num_heads;
+  p.num_seqs = num_seqs; p.q_len = q_len; p.kv_len = kv_len; p.num_heads = num_heads;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = (int)ldo;

@@ -77,7 +77,24 @@ def attention_qkv(qkv: torch.Tensor, out: torch.Tensor, num_seqs: int, seq_len: 
     assert qkv.shape[0] == num_seqs * seq_len and out.shape[0] == qkv.shape[0] and out.shape[1] == C
     ld = qkv.stride(0)
     rc = lib.pi3b_attn_fwd_hd64(_stream(), qkv.data_ptr(), qkv.data_ptr(), qkv.data_ptr(), ld, ld, ld, 0, C, 2 * C,
-                                out.data_ptr(), out.stride(0), num_seqs, seq_len, num_heads, scale)
+                                out.data_ptr(), out.stride(0), num_seqs, seq_len, seq_len, num_heads, scale)
+    _lib.check(rc, "pi3b_attn_fwd_hd64")
+    return out
+
+
+def attention_q_kv(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, num_seqs: int, q_len: int, kv_len: int,
+                   num_heads: int = 16, scale: float = 0.125, q_col0: int = 0) -> torch.Tensor:
+    """Attention of local queries against a separate key/value matrix (sequence-parallel global attention):
+    q: bf16 [num_seqs*q_len, >= q_col0 + heads*64] (queries at column q_col0 + 64*h), kv: bf16
+    [num_seqs*kv_len, 2*heads*64] (k | v, head-major), out: bf16 [num_seqs*q_len, heads*64]."""
+    lib = _lib.load()
+    _req(q, torch.bfloat16, "q"); _req(kv, torch.bfloat16, "kv"); _req(out, torch.bfloat16, "out")
+    C = num_heads * 64
+    assert q.stride(1) == 1 and kv.stride(1) == 1 and out.stride(1) == 1
+    assert q.shape[0] == num_seqs * q_len and kv.shape == (num_seqs * kv_len, 2 * C) and out.shape == (q.shape[0], C)
+    rc = lib.pi3b_attn_fwd_hd64(_stream(), q.data_ptr(), kv.data_ptr(), kv.data_ptr(), q.stride(0), kv.stride(0),
+                                kv.stride(0), q_col0, 0, C, out.data_ptr(), out.stride(0), num_seqs, q_len, kv_len,
+                                num_heads, scale)
     _lib.check(rc, "pi3b_attn_fwd_hd64")
     return out
 
