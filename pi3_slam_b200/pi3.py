@@ -217,8 +217,8 @@ class Pi3(nn.Module):
         self._shape_cache[key] = c
         return c
 
-    def _buffers_for(self, BN: int, H: int, W: int, device: torch.device) -> dict:
-        key = (BN, H, W, str(device))
+    def _buffers_for(self, BN: int, H: int, W: int, device: torch.device, sp_world: int = 1) -> dict:
+        key = (BN, H, W, str(device), sp_world)
         a = self._arena.get(key)
         if a is not None:
             return a
@@ -236,18 +236,29 @@ class Pi3(nn.Module):
             "feat_pts": e(M, K_PATCH), "feat_conf": e(M, PATCH * PATCH),
             "pooled": e(BN, 512), "pooled2": e(BN, 512), "rot9": e(BN, 12), "trans": e(BN, 4),
         }
+        if sp_world > 1:
+            a["kv_send"] = e(M, 2 * D, dt=bf)
+            a["kv_all"] = e(sp_world * M, 2 * D, dt=bf)
         self._arena = {key: a}   # one live shape at a time
         return a
 
     # ------------------------------------------------------------------ forward
-    def _block(self, x, b, bufs, num_seqs, seq_len, T, pw, cs, rope: bool) -> None:
-        """x += ls1 * proj(attn(LN(x)));  x += ls2 * fc2(GELU(fc1(LN(x))))   (block.py:333-334), in place on x."""
+    def _block(self, x, b, bufs, num_seqs, seq_len, T, pw, cs, rope: bool, sp_group=None) -> None:
+        """x += ls1 * proj(attn(LN(x)));  x += ls2 * fc2(GELU(fc1(LN(x))))   (block.py:333-334), in place on x.
+        With `sp_group` (sequence-parallel chunk-global layer) the local queries attend to the K/V rows of every
+        rank of the group, all-gathered over NCCL in frame order."""
         h, qkv, att, mlp = bufs["h"], bufs["qkv"], bufs["att"], bufs["mlp"]
         ops.layernorm(x, b["n1"][0], b["n1"][1], 1e-6, h)
         ops.gemm(h, b["qkv_w"], qkv, bias=b["qkv_b"])
         if rope or b["qn"] is not None:
             ops.qknorm_rope(qkv, HEADS, T, N_SPECIAL, pw, cs if rope else None, b["qn"], b["kn"], 1e-5)
-        if self.global_attn_events is not None and seq_len != T:
+        if sp_group is not None:
+            import torch.distributed as dist
+            G = dist.get_world_size(sp_group)
+            bufs["kv_send"].copy_(qkv[:, D:])                     # k | v of the local frames, made contiguous
+            dist.all_gather_into_tensor(bufs["kv_all"], bufs["kv_send"], group=sp_group)
+            ops.attention_q_kv(qkv, bufs["kv_all"], att, 1, seq_len, G * seq_len, HEADS, 0.125)
+        elif self.global_attn_events is not None and seq_len != T:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             ops.attention_qkv(qkv, att, num_seqs, seq_len, HEADS, 0.125)
@@ -261,9 +272,21 @@ class Pi3(nn.Module):
         ops.gemm(mlp, b["fc2_w"], x, bias=b["fc2_b"], gamma=b["ls2"], resid=x)
 
     @torch.no_grad()
-    def forward(self, imgs: torch.Tensor, taps: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+    def forward(self, imgs: torch.Tensor, taps: Optional[dict] = None, sp_group=None) -> Dict[str, torch.Tensor]:
+        """Reference signature `forward(imgs)`. Extension for over-long chunks: with `sp_group` (a
+        torch.distributed group, NCCL) `imgs` holds this rank's contiguous, equally sized slice of the chunk's
+        frames (rank order = frame order, B = 1); frame-local layers, MLPs and heads run locally, each of the 18
+        chunk-global layers all-gathers bf16 K and V across the group. Returns the local frames' outputs."""
         if imgs.dim() != 5 or imgs.shape[2] != 3:
             raise ValueError("imgs must be (B, N, 3, H, W)")
+        sp_world = 1
+        if sp_group is not None:
+            import torch.distributed as dist
+            sp_world = dist.get_world_size(sp_group)
+            if imgs.shape[0] != 1:
+                raise ValueError("sequence-parallel forward needs B == 1")
+            if sp_world == 1:
+                sp_group = None
         if not imgs.is_cuda:
             raise _lib.Pi3bError("pi3_slam_b200.Pi3 runs on CUDA (sm_100a) only; there is no CPU fallback")
         B, N, _, H, W = imgs.shape
@@ -277,7 +300,7 @@ class Pi3(nn.Module):
         T = P + N_SPECIAL
         BN = B * N
         M = BN * T
-        bufs = self._buffers_for(BN, H, W, device)
+        bufs = self._buffers_for(BN, H, W, device, sp_world)
         x = bufs["x"]
         imgs_f = imgs.reshape(BN, 3, H, W).to(torch.float32).contiguous()
 
@@ -302,7 +325,7 @@ class Pi3(nn.Module):
             if i % 2 == 0:
                 self._block(x, b, bufs, BN, T, T, pw, sc["cs"], rope=True)
             else:
-                self._block(x, b, bufs, B, N * T, T, pw, sc["cs"], rope=True)
+                self._block(x, b, bufs, B, N * T, T, pw, sc["cs"], rope=True, sp_group=sp_group)
             if taps is not None and i in (0, 1):
                 taps[f"dec_block{i}"] = x.view(BN, T, D).clone()
             if i == 34:

@@ -50,3 +50,20 @@ def test_attention_large_scores_lazy_rescale():
     ref = _ref(qkv, B, S, H)
     err = (out.float() - ref).norm() / ref.norm()
     assert err.item() < 1e-2, f"rel err {err.item():.3e}"
+
+
+def test_attention_local_queries_against_longer_kv():
+    """q_len != kv_len (sequence-parallel layout): a slice of the queries against all keys/values equals the
+    matching rows of the full attention."""
+    from pi3_slam_b200 import ops
+
+    S, H = 1100, 4
+    torch.manual_seed(11)
+    qkv = (torch.randn(S, 3 * H * 64, device="cuda") * 1.2).bfloat16()
+    ref = _ref(qkv, 1, S, H)
+    kv = qkv[:, H * 64:].contiguous()
+    for lo, hi in ((0, 300), (300, 829), (829, 1100)):
+        out = torch.empty(hi - lo, H * 64, device="cuda", dtype=torch.bfloat16)
+        ops.attention_q_kv(qkv[lo:hi], kv, out, 1, hi - lo, S, H)
+        err = (out.float() - ref[lo:hi]).norm() / ref[lo:hi].norm()
+        assert err.item() < 1e-2, f"rows {lo}:{hi} rel err {err.item():.3e}"
