@@ -40,7 +40,12 @@ struct GemmSmem {
   static constexpr int A_BYTES = kBlockM * 128;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  // per-epilogue-warp transpose staging: 32 rows x 16 fp32 (+4 pad so rows stay 16-byte aligned and the
+  // 128-bit accesses of 8 consecutive rows fall into distinct bank groups)
+  static constexpr int STG_STRIDE = 20;
+  static constexpr int STG_BYTES_PER_WARP = 32 * STG_STRIDE * 4;
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STG_OFFSET + kNumEpiWarps * STG_BYTES_PER_WARP;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024: manual alignment slack
 };
 
@@ -199,15 +204,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
             }
           }
-          if (row_ok) {
-            if (p.resid) {
-              const float4* rp = reinterpret_cast<const float4*>(p.resid + size_t(m) * p.ld_resid + n0);
+          if (p.resid) {
+            // fp32 read-modify-write of the residual stream: transpose through smem so that every global access is
+            // 64 contiguous bytes per row instead of 32 different rows per instruction (32 L1 wavefronts each).
+            // A/B on B200, fc2 + LayerScale + residual at M = 100400: 1203 -> 1284 TFLOP/s.
+            float* stg = reinterpret_cast<float*>(smem + S::STG_OFFSET + ew * S::STG_BYTES_PER_WARP);
+            const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 x = rp[j];
-                v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+            for (int h = 0; h < 2; ++h) {
+              float4* wr = reinterpret_cast<float4*>(stg + lane * S::STG_STRIDE);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                wr[j] = make_float4(v[h * 16 + 4 * j], v[h * 16 + 4 * j + 1], v[h * 16 + 4 * j + 2], v[h * 16 + 4 * j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + sub_r;
+                const int mi = m_blk * kBlockM + quarter * 32 + rr;
+                if (mi < p.M) {
+                  const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
+                  float4 x = *reinterpret_cast<const float4*>(stg + rr * S::STG_STRIDE + sub_c);
+                  const int col = n0 + h * 16 + sub_c;
+                  const float4 q = *reinterpret_cast<const float4*>(p.resid + size_t(mo) * p.ld_resid + col);
+                  x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+                  if (p.out_f32)
+                    *reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(mo) * p.ldo + col) = x;
+                  else
+                    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + size_t(mo) * p.ldo + col) =
+                        make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+                }
               }
+              __syncwarp();
             }
+          } else if (row_ok) {
             if (p.out_f32) {
               float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(m) * p.ldo + n0);
 #pragma unroll
