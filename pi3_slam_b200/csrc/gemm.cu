@@ -45,7 +45,10 @@ struct GemmSmem {
   static constexpr int STG_STRIDE = 20;
   static constexpr int STG_BYTES_PER_WARP = 32 * STG_STRIDE * 4;
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STG_OFFSET + kNumEpiWarps * STG_BYTES_PER_WARP;
+  // per-epilogue-warp copy of the bias / gamma slice of the current tile (fetched while the main loop runs)
+  static constexpr int BG_OFFSET = STG_OFFSET + kNumEpiWarps * STG_BYTES_PER_WARP;
+  static constexpr int BG_BYTES_PER_WARP = 2 * (BLOCK_N / 2) * 4;
+  static constexpr int BAR_OFFSET = BG_OFFSET + kNumEpiWarps * BG_BYTES_PER_WARP;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024: manual alignment slack
 };
 
@@ -168,6 +171,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int m_in = m_blk * kBlockM + quarter * 32 + lane;
       const bool row_ok = m_in < p.M;
       const int m = p.grp_in ? (m_in / p.grp_in) * p.grp_out + p.grp_off + m_in % p.grp_in : m_in;
+      // bias / gamma of this warp's columns go to smem BEFORE the accumulator is ready: their global-load latency
+      // (26 % of the epilogue warps' stall samples when loaded per chunk) hides under the main loop
+      float* bias_s = reinterpret_cast<float*>(smem + S::BG_OFFSET + ew * S::BG_BYTES_PER_WARP);
+      float* gamma_s = bias_s + COLS_PER_WARP;
+      if (p.vec_ok && lane * 4 < COLS_PER_WARP) {
+        const int mycol = n_blk * BLOCK_N + half * COLS_PER_WARP + lane * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (mycol + 3 < p.N) {
+          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + mycol));
+          if (p.gamma) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + mycol));
+        }
+        *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
+        *reinterpret_cast<float4*>(gamma_s + lane * 4) = g4;
+      }
+      __syncwarp();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -175,10 +193,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int col_in_tile = half * COLS_PER_WARP + c * 32;
         const int n0 = n_blk * BLOCK_N + col_in_tile;
         if (n0 >= p.N) break;  // warp-uniform
+        const int nvalid = min(32, p.N - n0);
+        // residual slice of this chunk in the transposed (coalesced) lane layout, requested before the accumulator
+        // chunk is read from TMEM: 8 x 16-byte loads in flight per lane (the RMW epilogue was latency-bound at
+        // 2.4 TB/s with 4 in flight and the loads issued after the math)
+        float4 rq[8];
+        const bool resid_fast = p.resid != nullptr && nvalid == 32 && p.vec_ok;
+        if (resid_fast) {
+#pragma unroll
+          for (int hi = 0; hi < 8; ++hi) {
+            const int mi = m_blk * kBlockM + quarter * 32 + (hi & 3) * 8 + (lane >> 2);
+            if (mi < p.M) {
+              const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
+              rq[hi] = *reinterpret_cast<const float4*>(p.resid + size_t(mo) * p.ld_resid + n0 + (hi >> 2) * 16 + (lane & 3) * 4);
+            }
+          }
+        }
         uint32_t r[32];
         tmem_ld_x32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N + col_in_tile, r);
         tmem_ld_wait();
-        const int nvalid = min(32, p.N - n0);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -186,7 +219,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              const float4 b = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
               v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
           }
@@ -200,7 +233,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (p.gamma) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + j));
+              const float4 g = *reinterpret_cast<const float4*>(gamma_s + c * 32 + j);
               v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
             }
           }
@@ -225,7 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
                   float4 x = *reinterpret_cast<const float4*>(stg + rr * S::STG_STRIDE + sub_c);
                   const int col = n0 + h * 16 + sub_c;
-                  const float4 q = *reinterpret_cast<const float4*>(p.resid + size_t(mo) * p.ld_resid + col);
+                  const float4 q = rq[h * 4 + it];
                   x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
                   if (p.out_f32)
                     *reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(mo) * p.ldo + col) = x;
