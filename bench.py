@@ -152,8 +152,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level
-        os.environ["NCCL_DEBUG"] = os.environ.get("PI3B_NCCL_DEBUG", "WARN")
+        # keep stdout to the single JSON line: NCCL writes its version banner / debug output to stdout by default
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     sd = make_state_dict(0)

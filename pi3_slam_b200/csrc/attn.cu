@@ -21,6 +21,18 @@
 //     group releases its S buffer as soon as the scores are in registers (s_free), so QK(j+1) is computed
 //     while the group is still busy with the exponentials of tile j;
 //   * ragged tails: KV columns past the sequence end are masked to -inf, Q rows past it are not stored.
+//
+// Measured anatomy of one softmax step (clock64 trace of CTA 0, -DPI3B_TRACE + scripts/trace_attn.py; 128 KV columns,
+// both Q tiles, ~2850 clocks): barrier wait + tcgen05 fence for S ~250, tcgen05.ld of the row ~250, max + exponentials
+// ~1650, wait for PV(j-1) ~230, tcgen05.st + fence + arrive ~200. The exponential phase is not MUFU-bound (its MUFU work
+// is ~900 clocks): ptxas places each MUFU.EX2's consumer 5-6 instructions behind it, warps issue in order, and with two
+// softmax warps per scheduler only ~1 MUFU per 14 clocks is issued. Variants measured on the same box and NOT kept
+// (all within 800-870 TFLOP/s at S = 100400): 16 softmax warps with column-split rows (MUFU saturates, but every warp
+// then sits in the ~1100-clock latency phase at the same time), one MMA issuer per Q tile with a half-step stagger,
+// consumers lagging one block behind the exponentials (ptxas re-interleaves them, also across bar.warp.sync), 64-column
+// steps with double / triple buffered S, intra-warp S prefetch, strict MUFU ping-pong via named barriers. Without any
+// exponentials the kernel reaches 1000 TFLOP/s, so the remaining gap to the tensor roofline is synchronisation latency,
+// not MUFU throughput or TMEM bandwidth.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -51,6 +63,17 @@ struct AttnParams {
   int ldo;
   float scale_log2;  // softmax scale * log2(e)
 };
+
+#ifdef PI3B_TRACE
+// debug-only timeline: CTA 0 writes clock64 stamps [role][iteration][event] into a global buffer
+__device__ unsigned long long* g_trace = nullptr;
+#define TRACE(role, it, ev)                                                                           \
+  do {                                                                                                \
+    if (blockIdx.x == 0 && lane == 0 && (it) < 64 && g_trace) g_trace[((role)*64 + (it)) * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define TRACE(role, it, ev) do {} while (0)
+#endif
 
 // TMEM column map
 constexpr uint32_t kTmS = 0;     // S tile t at kTmS + t*128   (128 fp32 columns)
@@ -222,13 +245,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int t = 0; t < num_t; ++t) {
             mbar_wait(&s_free[t], j & 1);  // softmax t holds S_t(j) in registers: the buffer can be refilled
             tc_fence_after();
+            TRACE(0, j, t);          // ev 0/1: s_free[t] observed
             issue_qk(t, sn);
+            TRACE(0, j, 2 + t);      // ev 2/3: QK(t, j+1) issued
           }
         }
         mbar_wait(&v_full[s], ph);
         for (int t = 0; t < num_t; ++t) {
           mbar_wait(&p_full[t], j & 1);  // P_t(j) is in TMEM
           tc_fence_after();
+          TRACE(0, j, 4 + t);        // ev 4/5: p_full[t] observed
           const uint32_t d = tmem_base + kTmO + t * 64;
           const uint32_t a = tmem_base + kTmP + t * 64;
           const uint64_t b0 = v_desc + uint64_t((s * kTileBytes) >> 4);
@@ -241,6 +267,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         if (elect_one()) umma_commit(&kv_empty[s]);  // QK(j) and PV(j) of both tiles have consumed stage s
         __syncwarp();
+        TRACE(0, j, 6);              // ev 6: iteration issued
       }
     }
   } else {
@@ -259,19 +286,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
       const uint64_t sc2 = pack2(sc, sc);
       uint64_t lsum = pack2(0.f, 0.f);
+      // A try_wait costs ~240 clocks even when the barrier has long completed (measured with the clock64 trace:
+      // 2 waits = 17 % of a softmax step). Both per-step barriers are therefore polled EARLY, while there is math
+      // to issue, and only waited on if the early poll failed.
+      bool s_ready = false;
       for (int j = 0; j < num_kv; ++j) {
-        mbar_wait(&s_full[t], j & 1);
+        if (quarter == 0) TRACE(1 + t, j, 0);   // ev 0: step start
+        if (!s_ready) mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
+        if (quarter == 0) TRACE(1 + t, j, 1);   // ev 1: S(j) ready
         uint32_t sr[128];
         tmem_ld_x32(tm_s, sr);
+#ifdef PI3B_DBG_NOLD
+#pragma unroll
+        for (int c = 32; c < 128; ++c) sr[c] = sr[c & 31] + c;   // roofline experiment: 1/4 of the TMEM reads
+#else
         tmem_ld_x32(tm_s + 32, sr + 32);
         tmem_ld_x32(tm_s + 64, sr + 64);
         tmem_ld_x32(tm_s + 96, sr + 96);
+#endif
         tmem_ld_wait();
         // the scores are in registers: hand the S buffer back so QK(j+1) runs under this step's exponentials
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[t]);
+        if (quarter == 0) TRACE(1 + t, j, 2);   // ev 2: S in registers, s_free arrived
+        // early poll: PV(j-1) was issued a whole step ago, its barrier is normally complete by now
+        bool pv_ready = (j == 0) || mbar_try_wait(&pv_done[t], (j - 1) & 1);
 
         const int kv_valid = p.kv_len - j * 128;
         if (kv_valid < 128) {
@@ -295,7 +336,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const bool grow = m_tile > m_used + 8.0f;
           if (__any_sync(0xffffffffu, grow)) {
             // O_t must be quiescent: PV(j-1) has finished
-            mbar_wait(&pv_done[t], (j - 1) & 1);
+            if (!pv_ready) mbar_wait(&pv_done[t], (j - 1) & 1);
+            pv_ready = true;
             tc_fence_after();
             float alpha = 1.0f;
             if (grow) {
@@ -324,19 +366,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint64_t x = ffma2(pack2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), sc2, negm2);
           float x0, x1;
           unpack2(x, x0, x1);
+#ifdef PI3B_DBG_NOEXP
+          const float p0 = x0;
+#else
           const float p0 = (kPolyEvery > 0 && (c % (2 * (kPolyEvery > 0 ? kPolyEvery : 1))) == 0) ? poly_exp2(x0) : fast_exp2(x0);
+#endif
+#ifdef PI3B_DBG_NOEXP
+          const float p1 = x1;                                   // roofline experiment: no MUFU work
+#else
           const float p1 = fast_exp2(x1);
+#endif
           lsum = fadd2(lsum, pack2(p0, p1));
           sr[c >> 1] = pack_bf16x2(p0, p1);
         }
+        if (quarter == 0) TRACE(1 + t, j, 3);   // ev 3: exponentials done
+        // early poll of the next S tile: QK(j+1) was issued when s_free(j) arrived, ~a whole math phase ago
+        s_ready = (j + 1 < num_kv) && mbar_try_wait(&s_full[t], (j + 1) & 1);
         // P_t was last read by PV(j-1): that MMA must have completed before the buffer is overwritten
-        if (j > 0) mbar_wait(&pv_done[t], (j - 1) & 1);
+        if (!pv_ready) mbar_wait(&pv_done[t], (j - 1) & 1);
+        tc_fence_after();
+        if (quarter == 0) TRACE(1 + t, j, 4);   // ev 4: PV(j-1) done
         tmem_st_x32(tm_p, sr);
         tmem_st_x32(tm_p + 32, sr + 32);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        if (quarter == 0) TRACE(1 + t, j, 5);   // ev 5: P stored, p_full arrived
       }
 
       // epilogue: O / l -> bf16 -> HBM
@@ -378,6 +434,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }  // namespace pi3b
 
 using namespace pi3b;
+
+#ifdef PI3B_TRACE
+extern "C" int pi3b_debug_set_trace(void* ptr) {
+  return cudaMemcpyToSymbol(g_trace, &ptr, sizeof(ptr)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
                                   int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo,
