@@ -193,3 +193,47 @@ def test_umeyama_kernel_and_chunk_alignment():
         expect = np.linalg.inv(gts[k]) @ gts[k + 1]              # qry frame -> ref frame
         assert np.abs(res["pairwise"][k].numpy() - expect).max() < 3e-2    # fp16 storage of the points
     assert res["cumulative"].shape == (3, 4, 4)
+
+
+def test_keypoints_disabled_stores_dense_maps(model, tmp_path):
+    """keypoint_type='none' (reference: offline_chunk_creator.py:81, Appendix B): dense maps are saved instead."""
+    from pi3_slam_b200.offline_chunk_creator import OfflineChunkCreator, OfflineCreatorConfig
+    from pi3_slam_b200.synthetic import make_frames
+    cfg = OfflineCreatorConfig(model_path="unused", output_dir=str(tmp_path), device="cuda", do_metric_depth=False,
+                               keypoint_type="none", estimate_camera_params=False)
+    cr = OfflineChunkCreator(cfg, model=model)
+    cr.target_size = (42, 56)
+    out = cr._process_single_chunk(make_frames(2, 42, 56)[None], [("a",), ("b",)])
+    assert out["points"].shape == (2, 42, 56, 3) and out["points"].dtype == torch.float32
+    assert out["conf"].shape == (2, 42, 56, 1) and out["masks"].shape == (2, 42, 56) and out["masks"].dtype == torch.bool
+    assert "keypoints" not in out and "camera_params" not in out and "intrinsics" not in out
+
+
+def test_metric_scale_branch_with_injected_depth_model(model, tmp_path):
+    """MoGe branch (reference :182-192) with a stand-in depth model: scale = lower median of moge_z / pi3_z over the
+    frame-0 mask; local_points, points and pose translations are scaled by it."""
+    from pi3_slam_b200.offline_chunk_creator import OfflineChunkCreator, OfflineCreatorConfig
+    from pi3_slam_b200.synthetic import make_frames
+
+    class FakeMoGe:
+        def infer(self, image):
+            H, W = image.shape[-2:]
+            g = torch.Generator(device="cpu").manual_seed(3)
+            return {"depth": (torch.rand(H, W, generator=g) * 2 + 1).to(image.device)}
+
+    imgs = make_frames(2, 42, 56)[None]
+    base_cfg = dict(model_path="unused", output_dir=str(tmp_path), device="cuda", keypoint_type="none",
+                    estimate_camera_params=False)
+    plain = OfflineChunkCreator(OfflineCreatorConfig(do_metric_depth=False, **base_cfg), model=model)
+    plain.target_size = (42, 56)
+    ref = plain._process_single_chunk(imgs, [("a",), ("b",)])
+    scaled = OfflineChunkCreator(OfflineCreatorConfig(do_metric_depth=True, **base_cfg), model=model, moge_model=FakeMoGe())
+    scaled.target_size = (42, 56)
+    out = scaled._process_single_chunk(imgs, [("a",), ("b",)])
+    depth = FakeMoGe().infer(imgs[0, 0].cuda())["depth"].cpu()
+    m0 = ref["masks"][0]
+    s = (depth[m0] / ref["local_points"][0][..., 2][m0]).median()
+    assert torch.allclose(out["local_points"], ref["local_points"] * s, rtol=1e-6)
+    assert torch.allclose(out["points"], ref["points"] * s, rtol=1e-6)
+    assert torch.allclose(out["camera_poses"][:, :3, 3], ref["camera_poses"][:, :3, 3] * s, rtol=1e-6)
+    assert torch.equal(out["camera_poses"][:, :3, :3], ref["camera_poses"][:, :3, :3])

@@ -125,3 +125,21 @@ def test_creator_rejects_cpu_device(tmp_path):
     assert cfg.chunk_length == 100 and cfg.overlap == 10 and cfg.keypoint_type == "aliked" and cfg.max_num_keypoints == 512
     with pytest.raises(Pi3bError):
         OfflineChunkCreator(cfg)
+
+
+def test_from_pretrained_reads_reference_style_directory(tmp_path):
+    """A directory as written by the reference's PyTorchModelHubMixin.save_pretrained: config.json + model.safetensors."""
+    from safetensors.torch import save_file
+    from pi3_slam_b200.pi3 import Pi3
+    from pi3_slam_b200.synthetic import pi3_param_shapes
+    shapes = pi3_param_shapes()
+    # small deterministic fill (ramps) — this test is about key / shape plumbing, not numerics
+    sd = {k: torch.full(shp, float(i % 7) * 0.01) for i, (k, shp) in enumerate(shapes.items())}
+    save_file(sd, str(tmp_path / "model.safetensors"))
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump({"pos_type": "rope100", "decoder_size": "large"}, f)
+    m = Pi3.from_pretrained(str(tmp_path))
+    got = m.state_dict()
+    for k in ("decoder.35.mlp.fc2.weight", "camera_head.fc_rot.bias", "encoder.pos_embed", "image_std"):
+        assert torch.equal(got[k], sd[k]), k
+    assert m.rope_freq == 100.0

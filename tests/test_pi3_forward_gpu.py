@@ -107,3 +107,31 @@ def test_cpu_input_is_rejected(model_and_sd):
     model, _ = model_and_sd
     with pytest.raises(Pi3bError):
         model(torch.rand(1, 2, 3, 28, 28))
+
+
+def test_single_frame_and_ragged_shapes(model_and_sd):
+    """N = 1 (chunk-global attention degenerates to the frame-local shape) and a non-square, odd patch grid."""
+    from oracle import pi3_oracle
+    from pi3_slam_b200.synthetic import make_frames
+
+    model, sd = model_and_sd
+    for n, h, w in ((1, 42, 70), (2, 70, 42)):
+        imgs = make_frames(n, h, w, start_index=7)[None]
+        out = model(imgs.cuda())
+        ref = pi3_oracle.pi3_forward(imgs, sd)
+        _check(out, ref, 1, f"oracle/{n}x{h}x{w}")
+
+
+def test_repeated_calls_are_deterministic_and_shape_switching_works(model_and_sd):
+    from pi3_slam_b200.synthetic import make_frames
+
+    model, _ = model_and_sd
+    a = make_frames(2, 42, 56)[None].cuda()
+    b = make_frames(3, 56, 42)[None].cuda()
+    r1 = {k: v.clone() for k, v in model(a).items()}
+    model(b)                      # different shape in between: arena / per-shape constants are rebuilt
+    r2 = model(a)
+    for k in r1:
+        assert torch.equal(r1[k], r2[k]), k
+    with pytest.raises(ValueError):
+        model(torch.rand(1, 2, 3, 40, 56, device="cuda"))      # H not a multiple of 14
