@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
 // (pi3.py:146-154). 8 lanes share one (row, head) so every access is a fully coalesced 16-byte vector;
 // the rotation partner sits 2 lanes away (shfl_xor 2). cs_table[pos][j] = (cos, sin) in fp32.
 // ------------------------------------------------------------------------------------------------
+constexpr int kQkRows = 4;  // rows per thread: 4 independent 16-byte loads in flight (the 1-row version was latency-bound at 2.7 TB/s)
+
 __global__ void __launch_bounds__(256) qknorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int M,
                                                           int num_heads, int tokens_per_frame, int n_special,
                                                           int patch_w, const float* __restrict__ qn_w,
@@ -94,67 +96,86 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(__nv_bfloat16* __restr
                                                           const float* __restrict__ kn_w,
                                                           const float* __restrict__ kn_b, float eps,
                                                           const float2* __restrict__ cs_table, int do_rope) {
-  const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int sub = int(gid & 7);
-  const int64_t unit = gid >> 3;  // (row, which, head)
-  const int heads2 = 2 * num_heads;
-  const int64_t row = unit / heads2;
-  if (row >= M) return;  // whole 8-lane groups exit together (M*heads2*8 threads are a multiple of 8)
-  const int hh = int(unit % heads2);
-  const int which = hh / num_heads;  // 0 = q, 1 = k
-  const int head = hh % num_heads;
-  __nv_bfloat16* ptr = qkv + row * ld + which * num_heads * 64 + head * 64 + sub * 8;
-  const uint4 raw = *reinterpret_cast<const uint4*>(ptr);
-  float x[8] = {bf_lo(raw.x), bf_hi(raw.x), bf_lo(raw.y), bf_hi(raw.y),
-                bf_lo(raw.z), bf_hi(raw.z), bf_lo(raw.w), bf_hi(raw.w)};
+  // 32-bit index math only: the first version spent most of its instructions in 64-bit divisions
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sub = int(gid & 7u);
+  const uint32_t unit = gid >> 3;  // (row group, which, head)
+  const uint32_t heads2 = 2u * uint32_t(num_heads);
+  const uint32_t grp = unit / heads2;
+  const int row0 = int(grp) * kQkRows;
+  if (row0 >= M) return;  // whole 8-lane groups exit together
+  const int hh = int(unit - grp * heads2);
+  const int which = hh >= num_heads ? 1 : 0;  // 0 = q, 1 = k
+  const int head = hh - which * num_heads;
+  __nv_bfloat16* base = qkv + which * num_heads * 64 + head * 64 + sub * 8;
+  uint4 raw[kQkRows];
+#pragma unroll
+  for (int r = 0; r < kQkRows; ++r)
+    if (row0 + r < M) raw[r] = *reinterpret_cast<const uint4*>(base + int64_t(row0 + r) * ld);
   const float* nw = which ? kn_w : qn_w;
   const float* nb = which ? kn_b : qn_b;
+  float w8[8], b8[8];
   if (nw) {
-    float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += x[i];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    const float mean = s * (1.0f / 64.0f);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q += (x[i] - mean) * (x[i] - mean);
-    q += __shfl_xor_sync(0xffffffffu, q, 1);
-    q += __shfl_xor_sync(0xffffffffu, q, 2);
-    q += __shfl_xor_sync(0xffffffffu, q, 4);
-    const float rstd = rsqrtf(q * (1.0f / 64.0f) + eps);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float y = (x[i] - mean) * rstd * __ldg(nw + sub * 8 + i) + __ldg(nb + sub * 8 + i);
-      x[i] = __bfloat162float(__float2bfloat16(y));  // reference casts the normed q/k to bf16 before RoPE
-    }
+    for (int i = 0; i < 8; ++i) { w8[i] = __ldg(nw + sub * 8 + i); b8[i] = __ldg(nb + sub * 8 + i); }
   }
-  if (do_rope) {
-    const int t = int(row % tokens_per_frame);
-    int pos = 0;
-    if (t >= n_special) {
-      const int pidx = t - n_special;
-      pos = (sub < 4 ? pidx / patch_w : pidx % patch_w) + 1;
-    }
-    const int sub4 = sub & 3;
-    const int j0 = (sub4 & 1) * 8;
-    const bool is_v = sub4 >= 2;  // second member of the (j, j+16) pair
-    float partner[8];
+  const int sub4 = sub & 3;
+  const int j0 = (sub4 & 1) * 8;
+  const bool is_v = sub4 >= 2;  // second member of the (j, j+16) pair
 #pragma unroll
-    for (int i = 0; i < 8; ++i) partner[i] = __shfl_xor_sync(0xffffffffu, x[i], 2);
-    if (pos != 0) {
-      const float2* cs = cs_table + size_t(pos) * 16 + j0;
+  for (int r = 0; r < kQkRows; ++r) {
+    const int row = row0 + r;
+    const bool ok = row < M;  // uniform inside an 8-lane group; shuffles below stay convergent for the full warp
+    float x[8] = {bf_lo(raw[r].x), bf_hi(raw[r].x), bf_lo(raw[r].y), bf_hi(raw[r].y),
+                  bf_lo(raw[r].z), bf_hi(raw[r].z), bf_lo(raw[r].w), bf_hi(raw[r].w)};
+    if (nw) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += x[i];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      const float mean = s * (1.0f / 64.0f);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q += (x[i] - mean) * (x[i] - mean);
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      q += __shfl_xor_sync(0xffffffffu, q, 4);
+      const float rstd = rsqrtf(q * (1.0f / 64.0f) + eps);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float2 c = __ldg(cs + i);
-        x[i] = is_v ? (x[i] * c.x + partner[i] * c.y) : (x[i] * c.x - partner[i] * c.y);
+        const float y = (x[i] - mean) * rstd * w8[i] + b8[i];
+        x[i] = __bfloat162float(__float2bfloat16(y));  // reference casts the normed q/k to bf16 before RoPE
       }
     }
+    if (do_rope) {
+      const int t = int(uint32_t(row) % uint32_t(tokens_per_frame));
+      int pos = 0;
+      if (ok && t >= n_special) {
+        const uint32_t pidx = uint32_t(t - n_special);
+        const uint32_t py = pidx / uint32_t(patch_w);
+        pos = int(sub < 4 ? py : pidx - py * uint32_t(patch_w)) + 1;
+      }
+      float partner[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) partner[i] = __shfl_xor_sync(0xffffffffu, x[i], 2);
+      if (pos != 0) {
+        const float4* cs = reinterpret_cast<const float4*>(cs_table + size_t(pos) * 16 + j0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 c = __ldg(cs + i);  // (cos, sin) of two consecutive frequencies
+          x[2 * i] = is_v ? (x[2 * i] * c.x + partner[2 * i] * c.y) : (x[2 * i] * c.x - partner[2 * i] * c.y);
+          x[2 * i + 1] = is_v ? (x[2 * i + 1] * c.z + partner[2 * i + 1] * c.w) : (x[2 * i + 1] * c.z - partner[2 * i + 1] * c.w);
+        }
+      }
+    }
+    if (ok) {
+      uint4 o;
+      o.x = bf16x2(x[0], x[1]); o.y = bf16x2(x[2], x[3]); o.z = bf16x2(x[4], x[5]); o.w = bf16x2(x[6], x[7]);
+      *reinterpret_cast<uint4*>(base + int64_t(row) * ld) = o;
+    }
   }
-  uint4 o;
-  o.x = bf16x2(x[0], x[1]); o.y = bf16x2(x[2], x[3]); o.z = bf16x2(x[4], x[5]); o.w = bf16x2(x[6], x[7]);
-  *reinterpret_cast<uint4*>(ptr) = o;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,7 +440,8 @@ extern "C" int pi3b_qknorm_rope(void* stream, void* qkv, int64_t ld, int M, int 
     const int ph = (tokens_per_frame - n_special + patch_w - 1) / patch_w;
     PI3B_REQUIRE(table_rows > (ph > patch_w ? ph : patch_w), "pi3b_qknorm_rope: cos/sin table too short");
   }
-  const int64_t threads = int64_t(M) * 2 * num_heads * 8;
+  const int64_t threads = int64_t((M + pi3b::kQkRows - 1) / pi3b::kQkRows) * 2 * num_heads * 8;
+  PI3B_REQUIRE(threads < (1ll << 31), "pi3b_qknorm_rope: too many rows");
   qknorm_rope_kernel<<<blocks_for(threads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<__nv_bfloat16*>(qkv), ld, M, num_heads, tokens_per_frame, n_special, patch_w, qn_w, qn_b, kn_w, kn_b,
       eps, reinterpret_cast<const float2*>(cs_table), do_rope);
