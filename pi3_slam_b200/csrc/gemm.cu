@@ -11,6 +11,8 @@
 // thread) and apply the fused epilogue  out = [resid +] gamma * act(acc + bias)  straight to HBM, so
 // the epilogue of tile i overlaps the main loop of tile i+1.  Operands: bf16 (kind::f16) or fp32 read
 // as TF32 (kind::tf32, used for the fp32 heads the reference runs with autocast disabled).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -54,7 +56,13 @@ struct GemmSmem {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-template <int BLOCK_N, int STAGES, bool TF32>
+// CL = 1: every CTA loads its own A (128 x K) and B (BLOCK_N x K) tiles.
+// CL = 2: thread-block clusters of two CTAs that work on vertically adjacent output tiles (same n block, m blocks
+//         2i and 2i+1). Each CTA loads its own A tile but only HALF of the shared B tile and TMA-multicasts that half
+//         into both CTAs, so a CTA pulls 32 KB instead of 48 KB through L2 per k block. Reason (ncu, qkv-shaped GEMM):
+//         the MMA warp spent 58 % of its time waiting on the TMA full barriers — with 192 KB of smem the ring holds
+//         just enough bytes in flight for 96 B/clk/SM at the loaded L2 latency; at 64 B/clk/SM it does.
+template <int BLOCK_N, int STAGES, bool TF32, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<BLOCK_N, STAGES>;
@@ -77,8 +85,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m * num_n;
   const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
+  // work units: CL = 1 -> output tiles; CL = 2 -> pairs of vertically adjacent tiles, one per CTA of the cluster
+  // (both CTAs walk the same unit sequence, so their pipelines stay in lock step; an odd last m block gives the second
+  // CTA an all-out-of-range tile: TMA zero-fills it and the epilogue stores nothing)
+  const int cta_rank = CL == 2 ? int(cluster_ctarank()) : 0;
+  const int num_tiles = ((num_m + CL - 1) / CL) * num_n;
+  const int unit0 = int(blockIdx.x) / CL;
+  const int unit_stride = int(gridDim.x) / CL;
+  auto tile_m = [&](int unit) { return (unit / num_n) * CL + cta_rank; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -87,7 +102,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);  // the slot is reused only when every CTA that receives multicast data has consumed it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -100,7 +115,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything remote touches them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -108,8 +124,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===== TMA producer: the whole warp walks the tile schedule, one elected lane issues (operands stay uniform) =====
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      const int m_blk = tile_m(tile), n_blk = tile % num_n;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
@@ -118,7 +134,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           // activations stream through once; the (small) weight panel is reused by every m block
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * kBlockM, kEvictNormal);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, kEvictLast);
+          if (CL == 2)  // my half of the B tile, delivered to both CTAs (the peer sends the other half)
+            tma_load_2d_mcast(sb + cta_rank * (S::B_BYTES / 2), &tmB, &full_bar[stage], kb * BLOCK_K,
+                              n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2), uint16_t(3), kEvictLast);
+          else
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, kEvictLast);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -133,7 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -149,7 +169,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             else
               umma_f16_ss(d_tmem, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot once these MMAs have read it (in both CTAs of a cluster: the peer multicasts into it)
+          if (CL == 2) umma_commit_mcast(&empty_bar[stage], uint16_t(3));
+          else umma_commit(&empty_bar[stage]);
           if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         }
         __syncwarp();
@@ -166,8 +188,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int COLS_PER_WARP = BLOCK_N / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      const int m_blk = tile_m(tile), n_blk = tile % num_n;
       const int m_in = m_blk * kBlockM + quarter * 32 + lane;
       const bool row_ok = m_in < p.M;
       const int m = p.grp_in ? (m_in / p.grp_in) * p.grp_out + p.grp_off + m_in % p.grp_in : m_in;
@@ -308,27 +330,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int BLOCK_N, int STAGES, bool TF32>
+template <int BLOCK_N, int STAGES, bool TF32, int CL>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
                        cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N, STAGES>;
-  auto kern = gemm_kernel<BLOCK_N, STAGES, TF32>;
+  auto kern = gemm_kernel<BLOCK_N, STAGES, TF32, CL>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
       return check_launch("gemm: cudaFuncSetAttribute");
     configured = true;
   }
-  const int num_tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + BLOCK_N - 1) / BLOCK_N);
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  kern<<<grid, kGemmThreads, S::TOTAL, stream>>>(tmA, tmB, p);
+  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int units = ((num_m + CL - 1) / CL) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  int grid = units * CL < num_sms ? units * CL : num_sms;
+  grid -= grid % CL;
+  if (CL == 1) {
+    kern<<<grid, kGemmThreads, S::TOTAL, stream>>>(tmA, tmB, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p) != cudaSuccess) return check_launch("gemm cluster launch");
+  }
   return check_launch("gemm launch");
 }
 
@@ -369,11 +410,14 @@ extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda,
   // Use the wide tile when it still fills the machine; otherwise the narrow tile for more CTAs.
   const int tiles256 = ((M + 127) / 128) * ((N + 255) / 256);
   const bool wide = tiles256 >= num_sms && N > 128;
+  // wide tiles run as 2-CTA clusters sharing the B tile through TMA multicast (PI3B_GEMM_CLUSTER=0 disables, for A/B runs)
+  static const bool cluster_ok = []() { const char* e = getenv("PI3B_GEMM_CLUSTER"); return !(e && e[0] == '0'); }();
+  const bool cluster = wide && cluster_ok && M > 128;
 
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(&tmA, A, in_dtype, (uint64_t)M, (uint64_t)K, (uint64_t)lda * esz, 128, block_k);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmB, W, in_dtype, (uint64_t)N, (uint64_t)K, (uint64_t)ldw * esz, wide ? 256 : 128, block_k);
+  rc = make_tmap_2d(&tmB, W, in_dtype, (uint64_t)N, (uint64_t)K, (uint64_t)ldw * esz, (wide && !cluster) ? 256 : 128, block_k);
   if (rc) return rc;
 
   GemmParams p;
@@ -384,8 +428,10 @@ extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda,
   p.grp_in = grp_in; p.grp_out = grp_out; p.grp_off = grp_off;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (in_dtype == 0) {
-    return wide ? launch_gemm<256, 4, false>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, false>(tmA, tmB, p, num_sms, st);
+    if (cluster) return launch_gemm<256, 4, false, 2>(tmA, tmB, p, num_sms, st);
+    return wide ? launch_gemm<256, 4, false, 1>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, false, 1>(tmA, tmB, p, num_sms, st);
   } else {
-    return wide ? launch_gemm<256, 4, true>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, true>(tmA, tmB, p, num_sms, st);
+    if (cluster) return launch_gemm<256, 4, true, 2>(tmA, tmB, p, num_sms, st);
+    return wide ? launch_gemm<256, 4, true, 1>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, true, 1>(tmA, tmB, p, num_sms, st);
   }
 }
