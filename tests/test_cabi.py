@@ -54,3 +54,13 @@ def test_kernels_are_blackwell_native():
     assert "HMMA.16816" not in sass      # no legacy mma.sync tensor path
     arch = subprocess.run(["cuobjdump", "-lelf", str(LIB_PATH)], capture_output=True, text=True).stdout
     assert "sm_100a" in arch
+
+
+def test_missing_library_fails_loudly():
+    """No silent fallback: if libpi3b200.so cannot be found the package raises instead of computing on the CPU."""
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['PI3B_LIB'] = '/nonexistent/libpi3b200.so';"
+            "from pi3_slam_b200 import _lib\n"
+            "try:\n    _lib.load()\nexcept _lib.Pi3bError as e:\n    print('RAISED', e)\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "RAISED" in out.stdout and "no CPU or PyTorch fallback" in out.stdout, out.stdout + out.stderr
