@@ -47,8 +47,9 @@ int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, const void* v
                        int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo, int num_seqs,
                        int q_len, int kv_len, int num_heads, float scale);
 
-/* out[M,1024] = LayerNorm(x[M,1024]) * gamma + beta (fp32 in; bf16 or fp32 out; in place allowed).
+/* out[M,D] = LayerNorm(x[M,D]) * gamma + beta (fp32 in; bf16 or fp32 out; in place allowed).
  * If override_rows != NULL, rows r with r % period < n_override are set to override_rows[r % period] instead.
+ * D = 384, 768 or 1024.
  * replaces: nn.LayerNorm(eps=1e-6) in pi3/models/dinov2/layers/block.py:88-113, pi3/models/layers/block.py:310-335,
  *   encoder norm + token slicing pi3/models/dinov2/models/vision_transformer.py:271-275 and the register-token
  *   concat of pi3/models/pi3.py:140-144. */
@@ -129,6 +130,48 @@ int pi3b_median_ratio(void* stream, const float* a, int a_stride, const float* b
  *   pt.math.Sim3d.exp(...).matrix() at utils/reconstruction_alignment.py:89-105 (un-vendored pytheia==0.2.9). */
 int pi3b_umeyama_sim3_batched(void* stream, const float* qry, const float* ref, const uint8_t* valid,
                               int num_problems, int n_per, float* out18);
+
+/* ---- MoGe metric-depth pass (row a15): dense-prediction pieces around pi3b_gemm. Feature maps are channels-last
+ * fp32 matrices [H*W, C] (row pitch ld, in elements). ---------------------------------------------------------- */
+
+/* GroupNorm statistics over one sample: mean_rstd[g] = (mean, 1/sqrt(var_biased + eps)) over C/groups channels x rows
+ * pixels. workspace: 2*groups doubles (zeroed by the call). groups <= 32, C <= 1024.
+ * replaces: nn.GroupNorm(1, C) / nn.GroupNorm(C/32, C) statistics in moge/model/modules.py:48-56. */
+int pi3b_groupnorm_stats(void* stream, const float* x, int64_t ldx, int64_t rows, int C, int groups, float eps,
+                         double* workspace, float* mean_rstd);
+
+/* out bf16 [H*W, ldo]: column t*C + c of row (y, x) = act(norm(x[clamp(y + t/3 - 1), clamp(x + t%3 - 1)][c])), t = 0..8:
+ * the A operand of a 3x3 / stride 1 / replicate-padded conv as a GEMM with W[Cout][t*C + c]. mean_rstd != NULL applies
+ * (v - mean_g) * rstd_g * gamma[c] + beta[c] first; relu != 0 applies max(., 0). blocked != 0: the source is the
+ * [H/2*W/2, 4*C] output of a 2x2 / stride-2 ConvTranspose GEMM (column block dy*2+dx = output pixel (2Y+dy, 2X+dx)).
+ * replaces: GroupNorm -> ReLU -> Conv2d(3x3, padding_mode='replicate') of ResidualConvBlock moge/model/modules.py:47-60
+ *   and the ConvTranspose2d -> Conv2d pair of Resampler('conv_transpose') moge/model/modules.py:160-165. */
+int pi3b_im2col3x3(void* stream, const float* x, int64_t ldx, int H, int W, int C, int blocked, const float* mean_rstd,
+                   int groups, const float* gamma, const float* beta, int relu, void* out, int64_t ldo);
+
+/* x[y*W + x', c] (+)= w[c*ldw]*u_tab[x'] + w[c*ldw + 1]*v_tab[y] + bias[c]   (accumulate != 0: +=, else =).
+ * replaces: the uv concat of moge/model/v2.py:141-147 followed by the 1x1 input conv moge/model/modules.py:208-211,245
+ *   (normalized_view_plane_uv moge/utils/geometry_torch.py:40-52 supplies u_tab / v_tab). */
+int pi3b_uv_affine(void* stream, float* x, int64_t ldx, int H, int W, int C, const float* w, int ldw, const float* bias,
+                   const float* u_tab, const float* v_tab, int accumulate);
+
+/* out(c, y, x) = sum_j wy[y*taps_y + j] * sum_i wx[x*taps_x + i] * in(c, min(y0[y] + j, Hi-1), min(x0[x] + i, Wi-1));
+ * element (c, y, x) sits at c*sc + y*sy + x*sx (elements). Tap tables are the caller's (ATen bilinear / bilinear-aa).
+ * replaces: F.interpolate(bilinear, antialias=True) moge/model/modules.py:121 and F.interpolate(bilinear)
+ *   moge/model/v2.py:157. */
+int pi3b_resample2d(void* stream, const float* in, int64_t in_sc, int64_t in_sy, int64_t in_sx, int Hi, int Wi, float* out,
+                    int64_t out_sc, int64_t out_sy, int64_t out_sx, int C, int Ho, int Wo, const int* y0, const float* wy,
+                    int taps_y, const int* x0, const float* wx, int taps_x);
+
+/* points [n,3] in place: mode 0 linear, 1 sinh, 2 exp (z = e^z; xy *= z), 3 sinh_exp; mask_prob = sigmoid(mask_logit)
+ * (both may be NULL). replaces: MoGeModel._remap_points + mask sigmoid moge/model/v2.py:112-126, 160-167. */
+int pi3b_moge_remap(void* stream, float* points, const float* mask_logit, float* mask_prob, int mode, int64_t n);
+
+/* z' = points[:,2] + shift; m = mask_prob > 0.5 && z' > 0; depth = (m || !apply_mask) ? z' * exp(*log_scale) : +inf;
+ * mask_out = m. mask_prob, log_scale (device scalar), mask_out may be NULL.
+ * replaces: the depth / mask / metric-scale tail of MoGeModel.infer moge/model/v2.py:236-275. */
+int pi3b_moge_depth(void* stream, const float* points, const float* mask_prob, float shift, const float* log_scale,
+                    int apply_mask, float* depth, uint8_t* mask_out, int64_t n);
 
 #ifdef __cplusplus
 }

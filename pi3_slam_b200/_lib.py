@@ -54,6 +54,19 @@ SIGNATURES = {
     "pi3b_median_ratio": (c_int, [_P, _P, c_int, _P, c_int, _P, c_int, _P]),
     # stream, qry, ref, valid, num_problems, n_per, out18
     "pi3b_umeyama_sim3_batched": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
+    # stream, x, ldx, rows, C, groups, eps, workspace(double[2*groups]), mean_rstd(float[2*groups])
+    "pi3b_groupnorm_stats": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, c_float, _P, _P]),
+    # stream, x, ldx, H, W, C, blocked, mean_rstd, groups, gamma, beta, relu, out, ldo
+    "pi3b_im2col3x3": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P, c_int64]),
+    # stream, x, ldx, H, W, C, w, ldw, bias, u_tab, v_tab, accumulate
+    "pi3b_uv_affine": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, c_int, _P, _P, _P, c_int]),
+    # stream, in, in_sc, in_sy, in_sx, Hi, Wi, out, out_sc, out_sy, out_sx, C, Ho, Wo, y0, wy, taps_y, x0, wx, taps_x
+    "pi3b_resample2d": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int64, c_int,
+                                c_int, c_int, _P, _P, c_int, _P, _P, c_int]),
+    # stream, points, mask_logit, mask_prob, mode, n
+    "pi3b_moge_remap": (c_int, [_P, _P, _P, _P, c_int, c_int64]),
+    # stream, points, mask_prob, shift, log_scale, apply_mask, depth, mask_out, n
+    "pi3b_moge_depth": (c_int, [_P, _P, _P, c_float, _P, c_int, _P, _P, c_int64]),
 }
 
 

@@ -21,46 +21,49 @@ __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u <<
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm over D = 1024 (reference: nn.LayerNorm(eps=1e-6) in dinov2/layers/block.py:88-113 and
-// layers/block.py:310-335; encoder final norm vision_transformer.py:271). One warp per row, the row
-// lives in registers (8 x float4 per lane), two-pass statistics in fp32 like torch.
+// LayerNorm over D = 128 * NV (1024 for the pi3 trunk; 384 / 768 for the MoGe ViT-S / ViT-B encoders)
+// (reference: nn.LayerNorm(eps=1e-6) in dinov2/layers/block.py:88-113 and layers/block.py:310-335; encoder
+// final norm vision_transformer.py:271). One warp per row, the row lives in registers (NV x float4 per
+// lane), two-pass statistics in fp32 like torch.
 // Optional row override: rows with (row % period) < n_override are replaced by override[row % period]
 // (used to drop the encoder's cls/register tokens and install the decoder's register tokens,
 // pi3.py:140-144, in the same pass).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restrict__ x, int64_t ldx,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, float eps, void* out,
-                                                            int64_t ldo, int out_f32, int M,
-                                                            const float* __restrict__ override_rows, int period,
-                                                            int n_override) {
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, void* out,
+                                                        int64_t ldo, int out_f32, int M,
+                                                        const float* __restrict__ override_rows, int period,
+                                                        int n_override) {
+  constexpr int D = NV * 128;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  float4 v[8];
+  float4 v[NV];
   if (override_rows && (row % period) < n_override) {
-    const float4* src = reinterpret_cast<const float4*>(override_rows + size_t(row % period) * 1024);
+    const float4* src = reinterpret_cast<const float4*>(override_rows + size_t(row % period) * D);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = src[i * 32 + lane];
+    for (int i = 0; i < NV; ++i) v[i] = src[i * 32 + lane];
   } else {
     const float4* src = reinterpret_cast<const float4*>(x + size_t(row) * ldx);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = src[i * 32 + lane];
+    for (int i = 0; i < NV; ++i) v[i] = src[i * 32 + lane];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    const float mean = warp_sum(s) * (1.0f / 1024.0f);
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / float(D));
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       q += (a * a + b * b) + (c * c + d * d);
     }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / 1024.0f) + eps);
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / float(D)) + eps);
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
       v[i].x = (v[i].x - mean) * rstd * g.x + b.x;
       v[i].y = (v[i].y - mean) * rstd * g.y + b.y;
@@ -71,11 +74,11 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
   if (out_f32) {
     float4* dst = reinterpret_cast<float4*>(static_cast<float*>(out) + size_t(row) * ldo);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dst[i * 32 + lane] = v[i];
+    for (int i = 0; i < NV; ++i) dst[i * 32 + lane] = v[i];
   } else {
     uint2* dst = reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + size_t(row) * ldo);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dst[i * 32 + lane] = make_uint2(bf16x2(v[i].x, v[i].y), bf16x2(v[i].z, v[i].w));
+    for (int i = 0; i < NV; ++i) dst[i * 32 + lane] = make_uint2(bf16x2(v[i].x, v[i].y), bf16x2(v[i].z, v[i].w));
   }
 }
 
@@ -420,10 +423,11 @@ extern "C" int pi3b_layernorm(void* stream, const float* x, int64_t ldx, const f
                               float eps, void* out, int64_t ldo, int out_f32, int M, int D,
                               const float* override_rows, int period, int n_override) {
   PI3B_REQUIRE(x && gamma && beta && out, "pi3b_layernorm: null pointer");
-  PI3B_REQUIRE(D == 1024, "pi3b_layernorm: only D = 1024 is built (got %d)", D);
+  PI3B_REQUIRE(D == 1024 || D == 768 || D == 384, "pi3b_layernorm: D must be 384, 768 or 1024 (got %d)", D);
   PI3B_REQUIRE(M > 0 && ldx % 4 == 0 && ldo % 4 == 0, "pi3b_layernorm: bad M/ld");
   PI3B_REQUIRE(!override_rows || (period > 0 && n_override >= 0 && n_override <= period), "pi3b_layernorm: bad override");
-  layernorm1024_kernel<<<blocks_for(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  auto kern = D == 1024 ? layernorm_kernel<8> : (D == 768 ? layernorm_kernel<6> : layernorm_kernel<3>);
+  kern<<<blocks_for(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, ldx, gamma, beta, eps, out, ldo, out_f32, M, override_rows, period > 0 ? period : 1, n_override);
   return check_launch("layernorm launch");
 }

@@ -47,7 +47,7 @@ class OfflineCreatorConfig:
     cam_dist_path: Optional[str] = None
     # --- additions (defaults keep the reference behaviour) ---
     keypoint_seed: Optional[int] = None     # per-chunk re-seeding => sharding-independent keypoints
-    moge_model_path: Optional[str] = None   # MoGe weights are not bundled; None => try hub id like the reference
+    moge_model_path: Optional[str] = None   # local MoGe checkpoint (model.pt); None => hub id like the reference
 
 
 class OfflineChunkCreator:
@@ -64,12 +64,13 @@ class OfflineChunkCreator:
         self.model: Pi3 = (model if model is not None else Pi3.from_pretrained(config.model_path))
         self.model = self.model.to(config.device).eval()
 
-        # MoGe metric depth: any object with .infer(image (3,H,W)) -> {"depth": (H,W)}; the reference loads
+        # MoGe metric depth (pi3_slam_b200.moge.MoGeModel, the sm_100a implementation of moge/model/v2.py; any object
+        # with .infer(image (3,H,W)) -> {"depth": (H,W)} is accepted). The reference loads
         # "Ruicheng/moge-2-vits-normal" from the hub and silently continues without it on failure (:70-79).
         self.moge_model = moge_model
         if self.moge_model is None and config.do_metric_depth:
             try:
-                from moge.model.v2 import MoGeModel  # type: ignore
+                from .moge import MoGeModel
                 src = config.moge_model_path or "Ruicheng/moge-2-vits-normal"
                 self.moge_model = MoGeModel.from_pretrained(src).to(config.device).eval()
                 print("   MoGe loaded for metric scaling")

@@ -288,3 +288,111 @@ def umeyama_sim3(qry: torch.Tensor, ref: torch.Tensor, valid: Optional[torch.Ten
                                        qry.shape[1], out.data_ptr())
     _lib.check(rc, "pi3b_umeyama_sim3_batched")
     return out[:, :16].reshape(-1, 4, 4), out[:, 16], out[:, 17]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MoGe metric-depth pass (row a15): dense-prediction pieces. Feature maps are channels-last fp32 [H*W, C].
+# ---------------------------------------------------------------------------------------------------------------
+def groupnorm_stats(x: torch.Tensor, groups: int, eps: float = 1e-5) -> torch.Tensor:
+    """(mean, rstd) per group of one sample's map x fp32 [pixels, C] -> fp32 [groups, 2] on the device."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    ws = torch.empty(2 * groups, device=x.device, dtype=torch.float64)
+    out = torch.empty(groups, 2, device=x.device, dtype=torch.float32)
+    rc = lib.pi3b_groupnorm_stats(_stream(), x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], groups, eps,
+                                  ws.data_ptr(), out.data_ptr())
+    _lib.check(rc, "pi3b_groupnorm_stats")
+    return out
+
+
+def im2col3x3(x: torch.Tensor, H: int, W: int, C: int, out: torch.Tensor, blocked: bool = False,
+              mean_rstd: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
+              beta: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """bf16 [H*W, 9C] operand of a 3x3 replicate-padded conv, with GroupNorm + ReLU fused into the gather.
+    blocked: x is the [H/2*W/2, 4C] output of a 2x2/stride-2 transposed-conv GEMM."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x"); _req(out, torch.bfloat16, "out")
+    assert x.dim() == 2 and x.stride(1) == 1 and out.stride(1) == 1 and out.shape == (H * W, 9 * C)
+    assert x.shape == ((H // 2) * (W // 2), 4 * C) if blocked else x.shape == (H * W, C)
+    groups = 0
+    if mean_rstd is not None:
+        _req(mean_rstd, torch.float32, "mean_rstd"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+        groups = mean_rstd.shape[0]
+    rc = lib.pi3b_im2col3x3(_stream(), x.data_ptr(), x.stride(0), H, W, C, 1 if blocked else 0, _ptr(mean_rstd), groups,
+                            _ptr(gamma), _ptr(beta), 1 if relu else 0, out.data_ptr(), out.stride(0))
+    _lib.check(rc, "pi3b_im2col3x3")
+    return out
+
+
+def uv_affine(x: torch.Tensor, H: int, W: int, w: torch.Tensor, bias: Optional[torch.Tensor], u_tab: torch.Tensor,
+              v_tab: torch.Tensor, accumulate: bool) -> torch.Tensor:
+    """x[p, c] (+)= w[c,0]*u[p % W] + w[c,1]*v[p // W] + bias[c]  (1x1 conv on the view-plane uv map)."""
+    lib = _lib.load()
+    for t, nm in ((x, "x"), (w, "w"), (u_tab, "u_tab"), (v_tab, "v_tab")):
+        _req(t, torch.float32, nm)
+    assert x.shape[0] == H * W and w.shape == (x.shape[1], 2)
+    assert u_tab.numel() == W and v_tab.numel() == H and w.stride(1) == 1
+    rc = lib.pi3b_uv_affine(_stream(), x.data_ptr(), x.stride(0), H, W, x.shape[1], w.data_ptr(), w.stride(0),
+                            _ptr(bias), u_tab.data_ptr(), v_tab.data_ptr(), 1 if accumulate else 0)
+    _lib.check(rc, "pi3b_uv_affine")
+    return x
+
+
+def resample2d(src: torch.Tensor, src_layout: str, dst: torch.Tensor, dst_layout: str, tab_y, tab_x) -> torch.Tensor:
+    """Separable resampling with tap tables (y0 int32 [Ho], wy fp32 [Ho, ty]) / (x0, wx). Layout 'chw' or 'hwc'."""
+    lib = _lib.load()
+    _req(src, torch.float32, "src"); _req(dst, torch.float32, "dst")
+    assert src.is_contiguous() and dst.is_contiguous() and src.dim() == 3 and dst.dim() == 3
+
+    def geom(t, layout):
+        if layout == "chw":
+            C, H, W = t.shape
+            return C, H, W, H * W, W, 1
+        H, W, C = t.shape
+        return C, H, W, 1, W * C, C
+    C, Hi, Wi, isc, isy, isx = geom(src, src_layout)
+    C2, Ho, Wo, osc, osy, osx = geom(dst, dst_layout)
+    (y0, wy), (x0, wx) = tab_y, tab_x
+    assert C == C2 and y0.numel() == Ho and x0.numel() == Wo and wy.shape[0] == Ho and wx.shape[0] == Wo
+    assert y0.dtype == torch.int32 and x0.dtype == torch.int32 and y0.is_cuda and wy.is_cuda and x0.is_cuda and wx.is_cuda
+    rc = lib.pi3b_resample2d(_stream(), src.data_ptr(), isc, isy, isx, Hi, Wi, dst.data_ptr(), osc, osy, osx, C, Ho, Wo,
+                             y0.data_ptr(), wy.data_ptr(), wy.shape[1], x0.data_ptr(), wx.data_ptr(), wx.shape[1])
+    _lib.check(rc, "pi3b_resample2d")
+    return dst
+
+
+MOGE_REMAP = {"linear": 0, "sinh": 1, "exp": 2, "sinh_exp": 3}
+
+
+def moge_remap(points: torch.Tensor, mask_logit: Optional[torch.Tensor], mask_prob: Optional[torch.Tensor], mode: str):
+    lib = _lib.load()
+    _req(points, torch.float32, "points")
+    assert points.is_contiguous() and points.shape[-1] == 3
+    n = points.numel() // 3
+    if mask_logit is not None:
+        _req(mask_logit, torch.float32, "mask_logit"); _req(mask_prob, torch.float32, "mask_prob")
+        assert mask_logit.numel() == n and mask_prob.numel() == n and mask_logit.is_contiguous() and mask_prob.is_contiguous()
+    rc = lib.pi3b_moge_remap(_stream(), points.data_ptr(), _ptr(mask_logit), _ptr(mask_prob), MOGE_REMAP[mode], n)
+    _lib.check(rc, "pi3b_moge_remap")
+    return points
+
+
+def moge_depth(points: torch.Tensor, mask_prob: Optional[torch.Tensor], shift: float, log_scale: Optional[torch.Tensor],
+               apply_mask: bool):
+    """depth (fp32) and mask (uint8) of MoGeModel.infer from remapped points [H,W,3]."""
+    lib = _lib.load()
+    _req(points, torch.float32, "points")
+    assert points.is_contiguous() and points.shape[-1] == 3
+    n = points.numel() // 3
+    depth = torch.empty(points.shape[:-1], device=points.device, dtype=torch.float32)
+    mask = torch.empty(points.shape[:-1], device=points.device, dtype=torch.uint8)
+    if mask_prob is not None:
+        _req(mask_prob, torch.float32, "mask_prob")
+        assert mask_prob.is_contiguous() and mask_prob.numel() == n
+    if log_scale is not None:
+        _req(log_scale, torch.float32, "log_scale")
+    rc = lib.pi3b_moge_depth(_stream(), points.data_ptr(), _ptr(mask_prob), float(shift), _ptr(log_scale),
+                             1 if apply_mask else 0, depth.data_ptr(), mask.data_ptr(), n)
+    _lib.check(rc, "pi3b_moge_depth")
+    return depth, mask

@@ -151,3 +151,153 @@ def make_frames(num_frames: int, height: int, width: int, start_index: int = 0) 
         g.manual_seed(1234 + start_index + i)
         out[i] = torch.rand(3, height, width, generator=g)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MoGe-2 (metric-depth pass). The reference builds MoGeModel(**checkpoint['model_config'])
+# (moge/model/v2.py:89-94) and the checkpoint is a hub download that is not in the repo, so the architecture
+# hyper-parameters below are a recorded synthetic choice in the shape of the published ViT-S model: DINOv2 ViT-S/14
+# encoder with the last 4 blocks projected and summed, a 5-level ConvStack neck fed with view-plane uv at every level,
+# points + mask ConvStack heads, an MLP scale head on the class token, 'exp' output remap.
+# ---------------------------------------------------------------------------------------------------------------
+MOGE_BACKBONES = {"dinov2_vits14": (384, 12, 6), "dinov2_vitb14": (768, 12, 12), "dinov2_vitl14": (1024, 24, 16)}
+
+
+def moge_synth_config() -> dict:
+    pyramid = [256, 128, 64, 32, 32]
+    stack = dict(resamplers=["conv_transpose"] * 4, num_res_blocks=[1, 1, 1, 1, 1])
+    return dict(
+        encoder=dict(backbone="dinov2_vits14", intermediate_layers=4, dim_out=384),
+        neck=dict(dim_in=[386, 2, 2, 2, 2], dim_res_blocks=[384, 256, 128, 64, 32], dim_out=list(pyramid), **stack),
+        points_head=dict(dim_in=list(pyramid), dim_res_blocks=list(pyramid), dim_out=[None, None, None, None, 3], **stack),
+        mask_head=dict(dim_in=list(pyramid), dim_res_blocks=list(pyramid), dim_out=[None, None, None, None, 1], **stack),
+        scale_head=dict(dims=[384, 384, 1]),
+        remap_output="exp",
+        num_tokens_range=[1200, 3600],
+    )
+
+
+def _per_level(v, n):
+    return list(v) if isinstance(v, (list, tuple)) else [v] * n
+
+
+def _conv_stack_shapes(prefix: str, cfg: dict, s: Dict[str, Tuple[int, ...]]) -> None:
+    """Keys of reference ConvStack (moge/model/modules.py:195-233) for resampler type 'conv_transpose'."""
+    res = cfg["dim_res_blocks"]
+    n = len(res)
+    hidden_mul = cfg.get("dim_times_res_block_hidden", 1)
+    for i, (din, dres) in enumerate(zip(_per_level(cfg["dim_in"], n), res)):
+        if din is not None:
+            s[f"{prefix}.input_blocks.{i}.weight"] = (dres, din, 1, 1)
+            s[f"{prefix}.input_blocks.{i}.bias"] = (dres,)
+    for i, (a, b, kind) in enumerate(zip(res[:-1], res[1:], _per_level(cfg["resamplers"], n - 1))):
+        if kind != "conv_transpose":
+            raise NotImplementedError(f"resampler '{kind}' (only 'conv_transpose' is built)")
+        s[f"{prefix}.resamplers.{i}.0.weight"] = (a, b, 2, 2)
+        s[f"{prefix}.resamplers.{i}.0.bias"] = (b,)
+        s[f"{prefix}.resamplers.{i}.1.weight"] = (b, b, 3, 3)
+        s[f"{prefix}.resamplers.{i}.1.bias"] = (b,)
+    for i, (dres, nb) in enumerate(zip(res, _per_level(cfg.get("num_res_blocks", 1), n))):
+        hid = hidden_mul * dres
+        for j in range(nb):
+            p = f"{prefix}.res_blocks.{i}.{j}.layers"
+            if cfg.get("res_block_in_norm", "layer_norm") != "none":
+                s[f"{p}.0.weight"] = (dres,)
+                s[f"{p}.0.bias"] = (dres,)
+            s[f"{p}.2.weight"] = (hid, dres, 3, 3)
+            s[f"{p}.2.bias"] = (hid,)
+            if cfg.get("res_block_hidden_norm", "group_norm") != "none":
+                s[f"{p}.3.weight"] = (hid,)
+                s[f"{p}.3.bias"] = (hid,)
+            s[f"{p}.5.weight"] = (dres, hid, 3, 3)
+            s[f"{p}.5.bias"] = (dres,)
+    for i, (dout, dres) in enumerate(zip(_per_level(cfg["dim_out"], n), res)):
+        if dout is not None:
+            s[f"{prefix}.output_blocks.{i}.weight"] = (dout, dres, 1, 1)
+            s[f"{prefix}.output_blocks.{i}.bias"] = (dout,)
+
+
+def moge_param_shapes(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
+    """Reference `MoGeModel(**cfg).state_dict()` layout (moge/model/v2.py:29-56, modules.py:71-97, 184-233)."""
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    enc = cfg["encoder"]
+    dim, depth, _ = MOGE_BACKBONES[enc["backbone"]]
+    s["encoder.image_mean"] = (1, 3, 1, 1)
+    s["encoder.image_std"] = (1, 3, 1, 1)
+    b = "encoder.backbone"
+    s[f"{b}.cls_token"] = (1, 1, dim)
+    s[f"{b}.pos_embed"] = (1, 1 + 37 * 37, dim)
+    s[f"{b}.mask_token"] = (1, dim)
+    s[f"{b}.patch_embed.proj.weight"] = (dim, 3, 14, 14)
+    s[f"{b}.patch_embed.proj.bias"] = (dim,)
+    for i in range(depth):
+        p = f"{b}.blocks.{i}"
+        s[f"{p}.norm1.weight"] = (dim,)
+        s[f"{p}.norm1.bias"] = (dim,)
+        s[f"{p}.attn.qkv.weight"] = (3 * dim, dim)
+        s[f"{p}.attn.qkv.bias"] = (3 * dim,)
+        s[f"{p}.attn.proj.weight"] = (dim, dim)
+        s[f"{p}.attn.proj.bias"] = (dim,)
+        s[f"{p}.ls1.gamma"] = (dim,)
+        s[f"{p}.norm2.weight"] = (dim,)
+        s[f"{p}.norm2.bias"] = (dim,)
+        s[f"{p}.mlp.fc1.weight"] = (4 * dim, dim)
+        s[f"{p}.mlp.fc1.bias"] = (4 * dim,)
+        s[f"{p}.mlp.fc2.weight"] = (dim, 4 * dim)
+        s[f"{p}.mlp.fc2.bias"] = (dim,)
+        s[f"{p}.ls2.gamma"] = (dim,)
+    s[f"{b}.norm.weight"] = (dim,)
+    s[f"{b}.norm.bias"] = (dim,)
+    il = enc["intermediate_layers"]
+    for i in range(il if isinstance(il, int) else len(il)):
+        s[f"encoder.output_projections.{i}.weight"] = (enc["dim_out"], dim, 1, 1)
+        s[f"encoder.output_projections.{i}.bias"] = (enc["dim_out"],)
+    for name in ("neck", "points_head", "mask_head", "normal_head"):
+        if cfg.get(name) is not None:
+            _conv_stack_shapes(name, cfg[name], s)
+    if cfg.get("scale_head") is not None:
+        dims = cfg["scale_head"]["dims"]
+        for i, (a, c) in enumerate(zip(dims[:-1], dims[1:])):
+            s[f"scale_head.{2 * i}.weight"] = (c, a)
+            s[f"scale_head.{2 * i}.bias"] = (c,)
+    return s
+
+
+def _fill_moge(key: str, shape: Tuple[int, ...], seed: int) -> torch.Tensor:
+    g = _gen("moge:" + key, seed)
+    if key == "encoder.image_mean":
+        return torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    if key == "encoder.image_std":
+        return torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    if key.endswith("cls_token") or key.endswith("mask_token"):
+        return torch.randn(shape, generator=g) * 0.02
+    if key.endswith("pos_embed"):
+        return torch.randn(shape, generator=g).clamp_(-2, 2) * 0.02
+    if key.endswith("ls1.gamma") or key.endswith("ls2.gamma"):
+        return 1.0 + 0.1 * torch.randn(shape, generator=g)
+    if len(shape) == 1 and (".norm" in key or ".layers.0." in key or ".layers.3." in key):
+        if key.endswith(".weight"):
+            return 1.0 + 0.05 * torch.randn(shape, generator=g)
+        return 0.02 * torch.randn(shape, generator=g)
+    if key.endswith(".bias"):
+        return 0.02 * torch.randn(shape, generator=g)
+    if len(shape) == 4 and "patch_embed" not in key:
+        # conv / transposed-conv kernels: unit-gain fan-in scaling so activations stay O(1) down the pyramid; the 2-channel
+        # uv input convs get O(1) weights so the view-plane coordinates visibly steer the output
+        fan_in = shape[1] * shape[2] * shape[3] if ".resamplers." not in key or key.endswith(".1.weight") else shape[0]
+        std = 1.0 / fan_in ** 0.5
+        if key.startswith("points_head.output_blocks"):
+            std *= 0.1      # keeps z = exp(raw) within about [0.3, 3] like a real scene
+        elif key.startswith("mask_head.output_blocks"):
+            std *= 0.5
+        return torch.randn(shape, generator=g) * std
+    if "patch_embed" in key:
+        return torch.randn(shape, generator=g) * 0.024
+    return torch.randn(shape, generator=g).clamp_(-2, 2) * 0.02
+
+
+def make_moge_state_dict(cfg: dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for k, shp in moge_param_shapes(cfg).items():
+        sd[k] = _fill_moge(k, shp, seed).float().contiguous()
+    return sd
