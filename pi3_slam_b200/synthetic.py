@@ -263,6 +263,11 @@ def moge_param_shapes(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
     return s
 
 
+_MOGE_UV_QUIET = ("neck.input_blocks.4.weight", "neck.resamplers.3.1.weight", "neck.res_blocks.4.0.layers.5.weight",
+                  "neck.output_blocks.4.weight", "points_head.input_blocks.4.weight", "points_head.resamplers.3.1.weight",
+                  "points_head.res_blocks.4.0.layers.5.weight")
+
+
 def _fill_moge(key: str, shape: Tuple[int, ...], seed: int) -> torch.Tensor:
     g = _gen("moge:" + key, seed)
     if key == "encoder.image_mean":
@@ -290,7 +295,21 @@ def _fill_moge(key: str, shape: Tuple[int, ...], seed: int) -> torch.Tensor:
             std *= 0.1      # keeps z = exp(raw) within about [0.3, 3] like a real scene
         elif key.startswith("mask_head.output_blocks"):
             std *= 0.5
-        return torch.randn(shape, generator=g) * std
+        w = torch.randn(shape, generator=g) * std
+        # A trained MoGe emits a perspective-consistent point map (xy / z ~ uv / focal); random weights do not, and the
+        # focal/shift solve of infer() (a 1-D LM with ftol 1e-3) is then degenerate — its answer is decided by rounding
+        # noise, in the reference as much as here. Give the synthetic net the linear uv -> xy path a trained one has:
+        # two channels of the finest level carry uv through the residual stream to the xy outputs.
+        if key in _MOGE_UV_QUIET:
+            w[:2] *= 0.02       # nothing else writes into the two uv-carrying channels
+        if key == "neck.input_blocks.4.weight":
+            w[0, 0, 0, 0], w[1, 1, 0, 0] = 3.0, 3.0
+        elif key in ("neck.output_blocks.4.weight", "points_head.input_blocks.4.weight"):
+            w[0, 0, 0, 0] = w[1, 1, 0, 0] = 1.0
+        elif key == "points_head.output_blocks.4.weight":
+            w[:2] *= 0.3
+            w[0, 0, 0, 0] = w[1, 1, 0, 0] = 1.0 / (3.0 * 1.2)       # focal 1.2 (relative to the half diagonal)
+        return w
     if "patch_embed" in key:
         return torch.randn(shape, generator=g) * 0.024
     return torch.randn(shape, generator=g).clamp_(-2, 2) * 0.02

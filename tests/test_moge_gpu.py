@@ -14,6 +14,8 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False          # the torch references below are meant to be fp32
+torch.backends.cuda.matmul.allow_tf32 = False
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -127,7 +129,7 @@ def test_resample2d_matches_interpolate(hi, wi, ho, wo):
     out = ops.resample2d(img, "chw", torch.empty(3, ho, wo, device="cuda"), "chw", dev(bilinear_aa_taps(hi, ho)),
                          dev(bilinear_aa_taps(wi, wo)))
     ref = F.interpolate(img[None], (ho, wo), mode="bilinear", align_corners=False, antialias=True)[0]
-    assert (out - ref).abs().max() < 2e-6
+    assert (out - ref).abs().max() < 1e-5       # ATen CUDA builds the same triangle weights with different fp32 rounding
     hwc = img.permute(1, 2, 0).contiguous()
     out = ops.resample2d(hwc, "hwc", torch.empty(ho, wo, 3, device="cuda"), "hwc", dev(bilinear_taps(hi, ho)),
                          dev(bilinear_taps(wi, wo)))
