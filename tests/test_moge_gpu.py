@@ -2,9 +2,10 @@
 kernels against torch fp32, the full MoGeModel forward / infer against the oracle and against the goldens produced by
 the real reference, and the creator's metric-scale step with the native MoGe model.
 
-Tolerances (bf16 tensor-core operands, fp32 accumulation, vs the fp32 reference): relative L2 2e-2 on the point map
-and 3e-2 on mask logits (the same class as the pi3 trunk: a 12-block ViT followed by ~45 bf16 convolutions);
-scale factor (median of depth ratios) 2e-2.
+Tolerances (bf16 tensor-core operands, fp32 accumulation, vs the fp32 reference): relative L2 1e-2 on the point map
+and on the metric depth (the pointmap tolerance of BASELINE.json's north_star; measured 3.5-3.9e-3), 3e-2 absolute on
+the mask probability (measured 1.5-1.8e-2; < 1 % of the pixels flip side of 0.5), 2e-2 on the chunk's scale factor
+(measured 3.5e-3).
 """
 import os
 
@@ -161,7 +162,7 @@ def test_moge_forward_and_infer_match_reference_golden(moge, case):
     e_mask = float((fwd["mask"][0].cpu() - gold["fwd_mask"]).abs().max())
     e_scale = abs(float(fwd["metric_scale"][0].cpu() / gold["metric_scale"]) - 1)
     print(f"moge {case}: points relL2 {e_pts:.2e}  mask prob max|d| {e_mask:.2e}  metric_scale rel {e_scale:.2e}")
-    assert e_pts < 2e-2 and e_mask < 3e-2 and e_scale < 1e-2
+    assert e_pts < 1e-2 and e_mask < 3e-2 and e_scale < 2e-3
     inf = model.infer(img, num_tokens=c["num_tokens"])
     depth, mask = inf["depth"].cpu(), inf["mask"].cpu()
     assert depth.shape == (c["H"], c["W"]) and mask.dtype == torch.bool
@@ -171,7 +172,7 @@ def test_moge_forward_and_infer_match_reference_golden(moge, case):
     e_depth = rel_l2(depth[both], gold["depth"][both])
     ratio = float((depth[both] / gold["depth"][both]).median())
     print(f"moge {case}: mask flips {flips:.2e}  depth relL2 {e_depth:.2e}  median ratio {ratio:.5f}")
-    assert flips < 1e-2 and abs(ratio - 1) < 2e-2 and e_depth < 4e-2
+    assert flips < 1e-2 and abs(ratio - 1) < 5e-3 and e_depth < 1e-2
     assert (inf["intrinsics"].cpu() - gold["intrinsics"]).abs().max() < 0.05 * gold["intrinsics"][1, 1]
 
 
@@ -189,7 +190,7 @@ def test_moge_infer_default_tokens_matches_oracle(moge):
     ratio = float((inf["depth"].cpu()[both] / ref["depth"][both]).median())
     e_depth = rel_l2(inf["depth"].cpu()[both], ref["depth"][both])
     print(f"moge 3600 tokens: mask flips {flips:.2e}  depth relL2 {e_depth:.2e}  median ratio {ratio:.5f}")
-    assert flips < 1e-2 and abs(ratio - 1) < 2e-2 and e_depth < 4e-2
+    assert flips < 1e-2 and abs(ratio - 1) < 5e-3 and e_depth < 1e-2
 
 
 def test_creator_metric_scale_with_native_moge(moge, tmp_path):
@@ -221,3 +222,49 @@ def test_creator_metric_scale_with_native_moge(moge, tmp_path):
     print(f"metric scale: native {got_scale:.5f}  oracle {ref_scale:.5f}")
     assert np.isfinite(got_scale) and abs(got_scale / ref_scale - 1) < 2e-2
     assert torch.allclose(out["camera_poses"][:, :3, 3], ref["camera_poses"][:, :3, 3] * got_scale, rtol=1e-4)
+
+
+def test_cfg4_shaped_end_to_end_with_moge_keypoints_and_sim3(moge, tmp_path):
+    """BASELINE configs[3] in miniature: EuRoC-shaped 752x480 frames (target 280x448), pi3 + native MoGe metric scale +
+    grid keypoints (max-kp 200) + Sim3 between consecutive chunks, through process_and_save and the chunk files."""
+    from oracle import chunk_oracle as co
+    from pi3_slam_b200.alignment import align_consecutive_chunks
+    from pi3_slam_b200.offline_chunk_creator import OfflineChunkCreator, OfflineCreatorConfig
+    from pi3_slam_b200.pi3 import Pi3
+    from pi3_slam_b200.synthetic import make_frames, make_state_dict
+    model, _, _ = moge
+    pi3 = Pi3()
+    pi3.load_state_dict(make_state_dict(0), strict=True)
+    pi3 = pi3.cuda().eval()
+    H, W, L, ov = 280, 448, 4, 2
+    cfg = OfflineCreatorConfig(model_path="unused", output_dir=str(tmp_path), device="cuda", do_metric_depth=True,
+                               keypoint_type="grid", max_num_keypoints=200, chunk_length=L, overlap=ov, keypoint_seed=7)
+    creator = OfflineChunkCreator(cfg, model=pi3, moge_model=model)
+    paths = [f"/data/euroc/{i:05d}.png" for i in range(8)]
+    index = {p: i for i, p in enumerate(paths)}
+    files = creator.process_and_save(paths, loader=lambda ps, ts: torch.cat([make_frames(1, *ts, start_index=index[p]) for p in ps]),
+                                     target_size=(H, W))
+    chunks = [torch.load(f, weights_only=False) for f in files]
+    # reference index math (datasets/image_datasets.py:41-47): (0,4) (2,6) (4,8) and a 2-frame tail (6,8)
+    assert len(chunks) == 4 and chunks[3]["points"].shape == (2, 200, 3)
+    chunks = chunks[:3]
+    assert all(c["points"].shape == (L, 200, 3) for c in chunks)
+    # metric scale was applied: same chunk without MoGe differs by one positive scalar on points and translations
+    plain = OfflineChunkCreator(OfflineCreatorConfig(model_path="unused", output_dir=str(tmp_path / "plain"), device="cuda",
+                                                     do_metric_depth=False, keypoint_type="grid", max_num_keypoints=200,
+                                                     chunk_length=L, overlap=ov, keypoint_seed=7), model=pi3)
+    files0 = plain.process_and_save(paths, loader=lambda ps, ts: torch.cat([make_frames(1, *ts, start_index=index[p]) for p in ps]),
+                                    target_size=(H, W))
+    c0 = torch.load(files0[0], weights_only=False)
+    assert torch.equal(c0["keypoints"], chunks[0]["keypoints"])
+    ratio = (chunks[0]["points"].float().norm(dim=-1) / c0["points"].float().norm(dim=-1)).flatten()
+    scale = float(ratio.median())
+    assert 0.05 < scale < 50 and float((ratio / scale - 1).abs().max()) < 5e-3      # fp16 storage
+    t_ratio = chunks[0]["camera_poses"][1:, :3, 3].norm(dim=-1) / c0["camera_poses"][1:, :3, 3].norm(dim=-1)
+    assert torch.allclose(t_ratio, torch.full_like(t_ratio, scale), rtol=5e-3)
+    # Sim3 chain on the saved chunks: device kernel == float64 oracle on the same files
+    res = align_consecutive_chunks(chunks, L, ov)
+    for k in range(2):
+        ref = co.chunk_pair_alignment(chunks[k], chunks[k + 1], L, ov)
+        assert np.abs(res["pairwise"][k].numpy() - ref).max() < 5e-3 * max(1.0, np.abs(ref).max())
+    print(f"cfg4-shaped: metric scale {scale:.4f}; pairwise Sim3 scales {[float(np.cbrt(np.linalg.det(p.numpy()[:3, :3]))) for p in res['pairwise']]}")
