@@ -29,6 +29,42 @@ def shard_chunks(num_chunks: int, rank: int, world_size: int) -> List[int]:
     return list(range(rank, num_chunks, world_size))
 
 
+def plan_waves(frames_per_chunk: Sequence[int], world_size: int, allow_sp: bool = True) -> List[List[Tuple[int, Tuple[int, ...]]]]:
+    """Hybrid schedule for a sequence of independent chunks on `world_size` GPUs.
+
+    Returns waves; each wave is a list of (chunk_index, ranks): while at least `world_size` chunks remain every rank
+    takes one whole chunk (no communication). When fewer remain, the ranks are split into k equal groups (k = the
+    largest divisor of world_size not above the number of remaining chunks) and each group runs ONE chunk
+    sequence-parallel (frames split over the group, K/V all-gathered in the chunk-global layers), so the last wave
+    does not leave GPUs idle: 13 chunks on 8 GPUs = 8 singles, then 4 chunks on 4 pairs, then the 40-frame tail on all
+    8 (makespan 1.53 chunk-times instead of 2). A chunk whose frame count is not divisible by the group size falls back
+    to the largest group size that divides it. With allow_sp=False this is plain round-robin sharding (chunk i on rank
+    i % world_size), identical to `shard_chunks`."""
+    n = len(frames_per_chunk)
+    waves: List[List[Tuple[int, Tuple[int, ...]]]] = []
+    nxt = 0
+    while nxt < n:
+        remaining = n - nxt
+        if remaining >= world_size or not allow_sp or world_size == 1:
+            take = min(world_size, remaining)
+            waves.append([(nxt + j, ((nxt + j) % world_size,) if not allow_sp else (j,)) for j in range(take)])
+            nxt += take
+            continue
+        k = max(d for d in range(1, remaining + 1) if world_size % d == 0)
+        g = world_size // k
+        wave = []
+        for j in range(k):
+            gj = g
+            while frames_per_chunk[nxt + j] % gj:
+                gj -= 1
+                while g % gj:
+                    gj -= 1
+            wave.append((nxt + j, tuple(range(j * g, j * g + gj))))
+        waves.append(wave)
+        nxt += k
+    return waves
+
+
 class ChunkImageDataset(Dataset):
     """Yields {'chunk' (N,3,H,W), 'start_idx', 'end_idx', 'chunk_paths'} like the reference dataset.
     `loader(paths, target_size) -> (N,3,H,W)` is injectable (synthetic frames in tests/bench)."""
@@ -48,6 +84,11 @@ class ChunkImageDataset(Dataset):
 
     def __len__(self) -> int:
         return len(self.chunk_indices)
+
+    def load_frames(self, start: int, end: int) -> torch.Tensor:
+        """Frames [start, end) of the sequence at the target size, (n,3,H,W) — a slice of a chunk for the
+        sequence-parallel ranks, which only need their own frames."""
+        return self._loader(self.image_paths[start:end], self.target_size)
 
     def __getitem__(self, idx: int) -> Dict:
         start, end = self.chunk_indices[idx]

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib, ops
 from .host.camera_estimation import estimate_camera_parameters_single_chunk
-from .host.datasets import ChunkImageDataset, shard_chunks
+from .host.datasets import ChunkImageDataset, plan_waves
 from .host.image_utils import calculate_target_size
 from .host.keypoints import create_keypoint_extractor
 from .pi3 import Pi3
@@ -48,6 +48,7 @@ class OfflineCreatorConfig:
     # --- additions (defaults keep the reference behaviour) ---
     keypoint_seed: Optional[int] = None     # per-chunk re-seeding => sharding-independent keypoints
     moge_model_path: Optional[str] = None   # local MoGe checkpoint (model.pt); None => hub id like the reference
+    sequence_parallel_tail: bool = True     # multi-GPU: run the last (partial) wave of chunks sequence-parallel
 
 
 class OfflineChunkCreator:
@@ -140,7 +141,51 @@ class OfflineChunkCreator:
             print(f"   ⏱️ Inference: {dt_inf:.3f}s for {num_frames} frames  ->  {fps:.2f} FPS")
             _metrics = {"infer_s": float(dt_inf), "num_frames": int(num_frames), "fps": float(fps)}
             self.last_device_seconds = float(ev0.elapsed_time(ev1) * 1e-3)
+            return self._finish_chunk(pi3_result, imgs_dev, chunk_paths, _metrics)
 
+    def _process_chunk_sequence_parallel(self, load_frames: Callable[[int, int], torch.Tensor], num_frames: int,
+                                         chunk_paths: List, ranks: Tuple[int, ...], group) -> Optional[Dict]:
+        """One chunk on a group of ranks (the tail waves of `plan_waves`): every rank runs the forward on its
+        contiguous slice of the frames with the chunk-global K/V all-gathered over NCCL (`Pi3.forward(sp_group=)`), the
+        per-frame outputs are all-gathered in frame order and the group's first rank does the post-processing and
+        returns the chunk dict (the other ranks return None). Outputs are bit-identical to the single-GPU forward."""
+        import torch.distributed as dist
+        dev = self.config.device
+        rank = dist.get_rank()
+        g = len(ranks)
+        li = ranks.index(rank)
+        n_loc = num_frames // g
+        leader = li == 0
+        with torch.no_grad():
+            t0 = time.time()
+            if leader:
+                imgs_dev = load_frames(0, num_frames)[None].to(dev, non_blocking=True)
+                local = imgs_dev[:, :n_loc]
+            else:
+                imgs_dev = None
+                local = load_frames(li * n_loc, (li + 1) * n_loc)[None].to(dev, non_blocking=True)
+            out = self.model(local.contiguous(), sp_group=group)
+            full = {}
+            for k in ("points", "local_points", "conf", "camera_poses"):
+                src = out[k][0].contiguous()
+                dst = torch.empty((num_frames,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+                dist.all_gather_into_tensor(dst, src, group=group)
+                full[k] = dst[None]
+            torch.cuda.synchronize()
+            dt_inf = max(1e-6, time.time() - t0)
+            if not leader:
+                return None
+            fps = num_frames / dt_inf
+            print(f"   ⏱️ Inference ({g}-way sequence-parallel): {dt_inf:.3f}s for {num_frames} frames  ->  {fps:.2f} FPS")
+            _metrics = {"infer_s": float(dt_inf), "num_frames": int(num_frames), "fps": float(fps), "sp_ranks": list(ranks)}
+            return self._finish_chunk(full, imgs_dev, chunk_paths, _metrics)
+
+    def _finish_chunk(self, pi3_result: Dict[str, torch.Tensor], imgs_dev: torch.Tensor, chunk_paths: List,
+                      _metrics: Dict) -> Dict:
+        """Everything of `_process_single_chunk` after the forward (reference :175-256), on the device."""
+        dev = self.config.device
+        num_frames = int(imgs_dev.shape[1])
+        with torch.no_grad():
             masks = self._compute_masks(pi3_result)[0]
 
             if self.moge_model is not None:
@@ -221,9 +266,11 @@ class OfflineChunkCreator:
 
     # ------------------------------------------------------------------ whole sequence
     def process_and_save(self, image_paths: Sequence, loader: Optional[Callable] = None,
-                         target_size: Optional[Tuple[int, int]] = None) -> List[str]:
+                         target_size: Optional[Tuple[int, int]] = None, distributed: Optional[bool] = None) -> List[str]:
         """Process the sequence in chunks and save one file per chunk; returns the files this rank wrote.
-        `loader` / `target_size` let synthetic (in-memory) sequences bypass image decoding."""
+        `loader` / `target_size` let synthetic (in-memory) sequences bypass image decoding. Under an initialised
+        torch.distributed (unless distributed=False) the chunks are scheduled over the ranks by `plan_waves`: whole
+        chunks per rank, and the last partial wave sequence-parallel over groups of ranks."""
         if not image_paths:
             raise ValueError("image_paths is empty")
         self.target_size = target_size or calculate_target_size(image_paths[0], pixel_limit=255000 // 2)
@@ -232,9 +279,17 @@ class OfflineChunkCreator:
         dataset = ChunkImageDataset(image_paths, self.config.chunk_length, self.config.overlap, self.target_size,
                                     device="cpu", loader=loader)
         rank, world = 0, 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        if distributed is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-        mine = shard_chunks(len(dataset), rank, world)
+        frames_per_chunk = [e - b for b, e in dataset.chunk_indices]
+        waves = plan_waves(frames_per_chunk, world, allow_sp=self.config.sequence_parallel_tail and world > 1)
+        # process groups of the sequence-parallel waves: created by every rank, in plan order (a collective)
+        groups: Dict[Tuple[int, ...], object] = {}
+        for wave in waves:
+            for _, ranks in wave:
+                if len(ranks) > 1 and ranks not in groups:
+                    groups[ranks] = torch.distributed.new_group(ranks=list(ranks))
+        mine = [(ci, ranks) for wave in waves for ci, ranks in wave if rank in ranks]
 
         saved_files: List[str] = []
         manifest: List[Dict] = []
@@ -243,18 +298,26 @@ class OfflineChunkCreator:
         per_chunk_fps: List[float] = []
         print(f"🔄 Processing {len(mine)} of {len(dataset)} chunks on rank {rank}/{world}...")
         pin = self.config.pin_memory
-        for chunk_idx in mine:
-            item = dataset[chunk_idx]
-            start_idx, end_idx = int(item["start_idx"].item()), int(item["end_idx"].item())
-            chunk_images = item["chunk"][None]
-            if pin:
-                chunk_images = chunk_images.pin_memory()
+        for chunk_idx, ranks in mine:
+            start_idx, end_idx = dataset.chunk_indices[chunk_idx]
             # default_collate turns the nested path list into 1-tuples (reference Appendix B)
-            chunk_paths = [(p,) for p in item["chunk_paths"][0]]
+            chunk_paths = [(p,) for p in dataset.image_paths[start_idx:end_idx]]
             print(f"📦 Chunk {chunk_idx + 1}/{len(dataset)}: frames {start_idx + 1}-{end_idx}")
             if self.config.keypoint_seed is not None:
                 torch.manual_seed(self.config.keypoint_seed + chunk_idx)
-            chunk_result = self._process_single_chunk(chunk_images, chunk_paths)
+            if len(ranks) > 1:
+                def load_frames(a: int, b: int, _s=start_idx) -> torch.Tensor:
+                    t = dataset.load_frames(_s + a, _s + b)
+                    return t.pin_memory() if pin else t
+                chunk_result = self._process_chunk_sequence_parallel(load_frames, end_idx - start_idx, chunk_paths, ranks,
+                                                                     groups[ranks])
+                if chunk_result is None:      # not the group's first rank: nothing to save
+                    continue
+            else:
+                chunk_images = dataset[chunk_idx]["chunk"][None]
+                if pin:
+                    chunk_images = chunk_images.pin_memory()
+                chunk_result = self._process_single_chunk(chunk_images, chunk_paths)
             m = chunk_result.get("_metrics", {})
             if m:
                 infer_times.append(float(m.get("infer_s", 0.0)))
@@ -284,7 +347,8 @@ class OfflineChunkCreator:
             print(f"   Steady-state FPS (full {self.config.chunk_length}-frame chunks, median): "
                   f"{steady[len(steady) // 2]:.2f} FPS")
 
-        manifest = self._gather_manifest(manifest)
+        if world > 1:
+            manifest = self._gather_manifest(manifest)
         if rank == 0:
             try:
                 with open(os.path.join(self.config.output_dir, "chunks_manifest.json"), "w") as f:

@@ -19,6 +19,16 @@ def _worker(rank, world, port, out_dir):
                  "num_frames": chunks[i][1] - chunks[i][0], "image_paths": [[f"f{j}"] for j in range(*chunks[i])]}
                 for i in mine]
     merged = OfflineChunkCreator._gather_manifest(manifest)
+    # hybrid schedule: the groups of the sequence-parallel tail wave are created collectively, in plan order
+    from pi3_slam_b200.host.datasets import plan_waves
+    waves = plan_waves([e - b for b, e in chunks], world)
+    tail = waves[-1]
+    assert tail == [(12, (0, 1))]
+    group = dist.new_group(ranks=list(tail[0][1]))
+    part = torch.full((2, 3), float(rank))
+    full = torch.empty(4, 3)
+    dist.all_gather_into_tensor(full, part, group=group)       # frame-ordered gather of per-frame outputs
+    assert full[:2].eq(0).all() and full[2:].eq(1).all()
     with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:
         json.dump({"mine": mine, "merged": merged}, f)
     dist.destroy_process_group()
@@ -33,3 +43,27 @@ def test_chunk_sharding_and_manifest_gather_world2(tmp_path):
     assert r0["merged"] == r1["merged"]
     assert [e["chunk_index"] for e in r0["merged"]] == list(range(13))
     assert r0["merged"][12]["start_idx"] == 960 and r0["merged"][12]["num_frames"] == 40
+
+
+def test_plan_waves_properties():
+    from pi3_slam_b200.host.datasets import chunk_index_list, plan_waves, shard_chunks
+    frames = [e - b for b, e in chunk_index_list(1000, 100, 20)]           # 12 x 100 + 40
+    for world in (1, 2, 4, 8):
+        waves = plan_waves(frames, world)
+        seen = [c for w in waves for c, _ in w]
+        assert seen == list(range(13))                                     # every chunk exactly once, in order
+        for w in waves:
+            used = [r for _, ranks in w for r in ranks]
+            assert len(used) == len(set(used)) and all(0 <= r < world for r in used)
+            assert all(frames[c] % len(ranks) == 0 for c, ranks in w)
+        # plain sharding when sequence parallelism is off
+        flat = plan_waves(frames, world, allow_sp=False)
+        for r in range(world):
+            assert [c for w in flat for c, ranks in w if ranks == (r,)] == shard_chunks(13, r, world)
+    w8 = plan_waves(frames, 8)
+    assert [len(w) for w in w8] == [8, 4, 1] and w8[1][0] == (8, (0, 1)) and w8[2][0][1] == tuple(range(8))
+    # makespan in chunk-times (cost ~ frames^2 for the dominant global attention; SP divides it by the group size)
+    cost = lambda wv: max((frames[c] / 100) ** 2 / len(r) for c, r in wv)          # noqa: E731
+    assert sum(cost(w) for w in w8) < 1.53 and sum(cost(w) for w in plan_waves(frames, 8, False)) == 2.0
+    # a chunk whose frame count does not divide falls back to a smaller group
+    assert plan_waves([100] * 5 + [37], 4)[-1] == [(4, (0, 1)), (5, (2,))]
