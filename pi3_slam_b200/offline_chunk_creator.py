@@ -92,6 +92,7 @@ class OfflineChunkCreator:
 
         self.target_size: Optional[Tuple[int, int]] = None
         self.undistortion_maps = None
+        self._sp_groups: Dict[Tuple[int, ...], object] = {}     # rank tuple -> process group of a sequence-parallel wave
         if getattr(config, "cam_dist_path", None):
             print("⚠️  cam_dist_path given: undistortion maps (cv2/pytheia) are outside this build; ignoring")
 
@@ -284,11 +285,13 @@ class OfflineChunkCreator:
         frames_per_chunk = [e - b for b, e in dataset.chunk_indices]
         waves = plan_waves(frames_per_chunk, world, allow_sp=self.config.sequence_parallel_tail and world > 1)
         # process groups of the sequence-parallel waves: created by every rank, in plan order (a collective)
-        groups: Dict[Tuple[int, ...], object] = {}
+        # (cached on the creator: an NCCL communicator costs ~0.5 s to build; the all-ranks group is the default one)
+        groups = self._sp_groups
         for wave in waves:
             for _, ranks in wave:
                 if len(ranks) > 1 and ranks not in groups:
-                    groups[ranks] = torch.distributed.new_group(ranks=list(ranks))
+                    groups[ranks] = (torch.distributed.group.WORLD if len(ranks) == world
+                                     else torch.distributed.new_group(ranks=list(ranks)))
         mine = [(ci, ranks) for wave in waves for ci, ranks in wave if rank in ranks]
 
         saved_files: List[str] = []

@@ -21,7 +21,8 @@ from pi3_slam_b200.synthetic import make_frames, make_state_dict  # noqa: E402
 
 
 def main():
-    a = [int(v) for v in sys.argv[1:6]]
+    skip_single = "nosingle" in sys.argv
+    a = [int(v) for v in sys.argv[1:6] if v != "nosingle"]
     frames, H, W, L, ov = a if len(a) == 5 else (20, 84, 112, 8, 2)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -32,7 +33,9 @@ def main():
     paths = [f"/synthetic/{i:05d}.png" for i in range(frames)]
     index = {p: i for i, p in enumerate(paths)}
     loader = lambda ps, ts: torch.cat([make_frames(1, *ts, start_index=index[p]) for p in ps])  # noqa: E731
-    root = os.environ.get("HYBRID_OUT") or tempfile.mkdtemp()
+    box = [os.environ.get("HYBRID_OUT") or tempfile.mkdtemp()]
+    dist.broadcast_object_list(box, src=0)          # every rank writes under rank 0's directory
+    root = box[0]
     base = dict(model_path="unused", device="cuda", do_metric_depth=False, keypoint_type="grid", max_num_keypoints=200,
                 chunk_length=L, overlap=ov, keypoint_seed=5)
     out = {"world": world, "frames": frames, "size": [H, W], "chunk": [L, ov]}
@@ -42,13 +45,17 @@ def main():
     for mode, sp in (("hybrid", True), ("round_robin", False)):
         cr = OfflineChunkCreator(OfflineCreatorConfig(output_dir=os.path.join(root, mode), sequence_parallel_tail=sp, **base),
                                  model=model)
-        for rep in range(2):                      # first pass warms allocations / NCCL
+        for rep in range(2 if mode == "hybrid" else 1):     # first pass warms allocations / NCCL communicators
             dist.barrier(); torch.cuda.synchronize(); t0 = time.time()
             cr.process_and_save(paths, loader=loader, target_size=(H, W))
             dist.barrier(); torch.cuda.synchronize()
             times[mode] = time.time() - t0
     out["makespan_s"] = times
-    if rank == 0:
+    if rank == 0 and skip_single:
+        out["total_frames_processed"] = sum(e - b for b, e in chunks)
+        out["frames_per_s"] = {k: out["total_frames_processed"] / v for k, v in times.items()}
+        print(json.dumps(out))
+    elif rank == 0:
         single = OfflineChunkCreator(OfflineCreatorConfig(output_dir=os.path.join(root, "single"), **base), model=model)
         t0 = time.time()
         files = single.process_and_save(paths, loader=loader, target_size=(H, W), distributed=False)
