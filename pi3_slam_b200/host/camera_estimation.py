@@ -66,26 +66,43 @@ def recover_focal_shift_from_samples(pts: np.ndarray, valid: np.ndarray, uv_lr: 
     return np.asarray(focal, dtype=np.float32), np.asarray(shift, dtype=np.float32)
 
 
-def estimate_camera_parameters_single_chunk(local_points: torch.Tensor, conf: torch.Tensor,
-                                            downsample_size: Tuple[int, int] = (64, 64)) -> Dict[str, torch.Tensor]:
-    """local_points (N,H,W,3), conf (N,H,W,1) on the device -> dict like the reference's
-    estimate_camera_parameters_single_chunk: intrinsics (N,3,3); focal/shift/fx/fy/cx/cy (1,N), on the device."""
+_SAMPLE_CACHE: Dict[tuple, tuple] = {}
+
+
+def sample_for_intrinsics(local_points: torch.Tensor, conf: torch.Tensor,
+                          downsample_size: Tuple[int, int] = (64, 64)):
+    """Device half of the intrinsics estimate: the 64x64 nearest samples (N, S, 3) and their validity
+    (sigmoid(conf) > 0.1) (N, S) uint8, both still on the device, plus the matching uv samples (S, 2) numpy."""
     N, H, W = local_points.shape[:3]
     dev = local_points.device
-    ys = nearest_indices(H, downsample_size[0])
-    xs = nearest_indices(W, downsample_size[1])
-    pts, val = ops.sample_grid(local_points, conf, torch.from_numpy(ys).to(dev), torch.from_numpy(xs).to(dev), 0.1)
-    uv = normalized_view_plane_uv(W, H)
-    uv_lr = uv[ys][:, xs].reshape(-1, 2)
-    focal_np, shift_np = recover_focal_shift_from_samples(pts.cpu().numpy(), val.cpu().numpy().astype(bool), uv_lr)
-    focal = torch.from_numpy(focal_np).to(dev).reshape(1, N)
-    shift = torch.from_numpy(shift_np).to(dev).reshape(1, N)
+    key = (H, W, tuple(downsample_size), str(dev))
+    c = _SAMPLE_CACHE.get(key)
+    if c is None:
+        # per-shape constants, uploaded once: a pageable host->device copy makes the driver wait for all the work
+        # already queued on the stream, which would serialise the host behind the chunk's forward
+        ys = nearest_indices(H, downsample_size[0])
+        xs = nearest_indices(W, downsample_size[1])
+        c = (torch.from_numpy(ys).to(dev), torch.from_numpy(xs).to(dev),
+             normalized_view_plane_uv(W, H)[ys][:, xs].reshape(-1, 2))
+        _SAMPLE_CACHE[key] = c
+    pts, val = ops.sample_grid(local_points, conf, c[0], c[1], 0.1)
+    return pts, val, c[2]
+
+
+def camera_parameters_from_samples(pts: np.ndarray, valid: np.ndarray, uv_lr: np.ndarray, H: int, W: int,
+                                   device="cpu") -> Dict[str, torch.Tensor]:
+    """Host half: per-frame LM solve + the reference's focal -> (fx, fy, cx, cy, K) formulas
+    (camera_estimation.py:47-60). Returns the reference-shaped dict: intrinsics (N,3,3); the rest (1,N)."""
+    N = pts.shape[0]
+    focal_np, shift_np = recover_focal_shift_from_samples(pts, valid.astype(bool), uv_lr)
+    focal = torch.from_numpy(focal_np).to(device).reshape(1, N)
+    shift = torch.from_numpy(shift_np).to(device).reshape(1, N)
     aspect = W / H
     fx = focal / 2 * (1 + aspect ** 2) ** 0.5 / aspect * W
     fy = focal / 2 * (1 + aspect ** 2) ** 0.5 * H
     cx = torch.full_like(fx, W // 2)
     cy = torch.full_like(fy, H // 2)
-    K = torch.zeros(1, N, 3, 3, device=dev, dtype=fx.dtype)
+    K = torch.zeros(1, N, 3, 3, device=device, dtype=fx.dtype)
     K[..., 0, 0] = fx
     K[..., 1, 1] = fy
     K[..., 0, 2] = cx
@@ -93,3 +110,12 @@ def estimate_camera_parameters_single_chunk(local_points: torch.Tensor, conf: to
     K[..., 2, 2] = 1.0
     # the reference squeezes the batch dim only from tensors with >= 3 dims (camera_estimation.py:127-130)
     return {"intrinsics": K.squeeze(0), "focal": focal, "shift": shift, "fx": fx, "fy": fy, "cx": cx, "cy": cy}
+
+
+def estimate_camera_parameters_single_chunk(local_points: torch.Tensor, conf: torch.Tensor,
+                                            downsample_size: Tuple[int, int] = (64, 64)) -> Dict[str, torch.Tensor]:
+    """local_points (N,H,W,3), conf (N,H,W,1) on the device -> dict like the reference's
+    estimate_camera_parameters_single_chunk: intrinsics (N,3,3); focal/shift/fx/fy/cx/cy (1,N), on the device."""
+    H, W = local_points.shape[1:3]
+    pts, val, uv_lr = sample_for_intrinsics(local_points, conf, downsample_size)
+    return camera_parameters_from_samples(pts.cpu().numpy(), val.cpu().numpy(), uv_lr, H, W, device=local_points.device)

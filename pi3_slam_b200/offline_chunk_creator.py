@@ -23,7 +23,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib, ops
-from .host.camera_estimation import estimate_camera_parameters_single_chunk
+from .host.camera_estimation import camera_parameters_from_samples, sample_for_intrinsics
 from .host.datasets import ChunkImageDataset, plan_waves
 from .host.image_utils import calculate_target_size
 from .host.keypoints import create_keypoint_extractor
@@ -49,6 +49,49 @@ class OfflineCreatorConfig:
     keypoint_seed: Optional[int] = None     # per-chunk re-seeding => sharding-independent keypoints
     moge_model_path: Optional[str] = None   # local MoGe checkpoint (model.pt); None => hub id like the reference
     sequence_parallel_tail: bool = True     # multi-GPU: run the last (partial) wave of chunks sequence-parallel
+
+
+class _PendingChunk:
+    """A chunk whose device work is enqueued: `finish()` waits for its event, runs the host half (per-frame scipy LM
+    for the intrinsics, dict assembly in the reference's key order / dtypes) and returns the chunk dict."""
+
+    def __init__(self, creator: "OfflineChunkCreator", chunk_paths: List, metrics: Dict, fwd_events=None):
+        self.creator, self.chunk_paths, self.metrics, self.fwd_events = creator, chunk_paths, metrics, fwd_events
+        self.staged: Dict[str, torch.Tensor] = {}      # pinned host tensors, valid after `event`
+        self.host: Dict[str, torch.Tensor] = {}        # already-final host tensors
+        self.intr = None
+        self.event: Optional[torch.cuda.Event] = None
+
+    def finish(self) -> Dict:
+        self.event.synchronize()
+        cr = self.creator
+        if self.fwd_events is not None:                # deferred timing print of the pipelined path
+            t0, ev0, ev1, num_frames = self.fwd_events
+            dev_s = float(ev0.elapsed_time(ev1) * 1e-3)
+            cr.last_device_seconds = dev_s
+            self.metrics.update(infer_s=dev_s, fps=num_frames / max(dev_s, 1e-6))
+            print(f"   ⏱️ Inference: {dev_s:.3f}s for {num_frames} frames  ->  {self.metrics['fps']:.2f} FPS")
+        camera_params = None
+        if self.intr is not None:
+            try:
+                pts, val, uv_lr, H, W = self.intr
+                camera_params = camera_parameters_from_samples(pts.numpy(), val.numpy(), uv_lr, H, W)
+            except Exception as e:
+                print(f"⚠️  Camera parameter estimation failed: {e}")
+        result: Dict = {"camera_poses": self.staged["camera_poses"], "image_paths": self.chunk_paths,
+                        "_metrics": self.metrics}
+        if camera_params is not None:
+            result["camera_params"] = camera_params
+        if cr.target_size is not None:
+            result["original_width"] = cr.target_size[1]
+            result["original_height"] = cr.target_size[0]
+        for k in ("points", "local_points", "conf", "masks", "keypoints", "descriptors", "scores", "colors"):
+            v = self.staged.get(k, self.host.get(k))
+            if v is not None:
+                result[k] = v.to(torch.float16) if k == "colors" else v
+        if result.get("camera_params") is not None:
+            result["intrinsics"] = result["camera_params"].get("intrinsics", None)
+        return result
 
 
 class OfflineChunkCreator:
@@ -144,12 +187,13 @@ class OfflineChunkCreator:
             self.last_device_seconds = float(ev0.elapsed_time(ev1) * 1e-3)
             return self._finish_chunk(pi3_result, imgs_dev, chunk_paths, _metrics)
 
-    def _process_chunk_sequence_parallel(self, load_frames: Callable[[int, int], torch.Tensor], num_frames: int,
+    def _process_chunk_sequence_parallel(self, frames_host: torch.Tensor, num_frames: int,
                                          chunk_paths: List, ranks: Tuple[int, ...], group) -> Optional[Dict]:
         """One chunk on a group of ranks (the tail waves of `plan_waves`): every rank runs the forward on its
         contiguous slice of the frames with the chunk-global K/V all-gathered over NCCL (`Pi3.forward(sp_group=)`), the
         per-frame outputs are all-gathered in frame order and the group's first rank does the post-processing and
-        returns the chunk dict (the other ranks return None). Outputs are bit-identical to the single-GPU forward."""
+        returns the chunk dict (the other ranks return None). Outputs are bit-identical to the single-GPU forward.
+        `frames_host`: all `num_frames` frames on the group's first rank, this rank's slice on the others."""
         import torch.distributed as dist
         dev = self.config.device
         rank = dist.get_rank()
@@ -160,11 +204,11 @@ class OfflineChunkCreator:
         with torch.no_grad():
             t0 = time.time()
             if leader:
-                imgs_dev = load_frames(0, num_frames)[None].to(dev, non_blocking=True)
+                imgs_dev = frames_host[None].to(dev, non_blocking=True)
                 local = imgs_dev[:, :n_loc]
             else:
                 imgs_dev = None
-                local = load_frames(li * n_loc, (li + 1) * n_loc)[None].to(dev, non_blocking=True)
+                local = frames_host[None].to(dev, non_blocking=True)
             out = self.model(local.contiguous(), sp_group=group)
             full = {}
             for k in ("points", "local_points", "conf", "camera_poses"):
@@ -183,9 +227,23 @@ class OfflineChunkCreator:
 
     def _finish_chunk(self, pi3_result: Dict[str, torch.Tensor], imgs_dev: torch.Tensor, chunk_paths: List,
                       _metrics: Dict) -> Dict:
-        """Everything of `_process_single_chunk` after the forward (reference :175-256), on the device."""
+        """Everything of `_process_single_chunk` after the forward (reference :175-256)."""
+        return self._enqueue_finish(pi3_result, imgs_dev, chunk_paths, _metrics).finish()
+
+    def _enqueue_finish(self, pi3_result: Dict[str, torch.Tensor], imgs_dev: torch.Tensor, chunk_paths: List,
+                        _metrics: Dict, fwd_events=None) -> "_PendingChunk":
+        """Device half of the post-processing: masks, metric scale, the 64x64 samples for the intrinsics solve, the
+        keypoint gather, and asynchronous copies of the (small) results into pinned host memory, closed by an event.
+        Nothing here waits for the GPU (except the MoGe pass, whose focal/shift solve is a host step), so the caller can
+        enqueue the next chunk's forward before `finish()` does the host half (scipy, dict assembly)."""
         dev = self.config.device
         num_frames = int(imgs_dev.shape[1])
+        pend = _PendingChunk(self, chunk_paths, _metrics, fwd_events)
+
+        def stage(t: torch.Tensor) -> torch.Tensor:
+            dst = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            dst.copy_(t, non_blocking=True)
+            return dst
         with torch.no_grad():
             masks = self._compute_masks(pi3_result)[0]
 
@@ -198,25 +256,13 @@ class OfflineChunkCreator:
                 pi3_result["camera_poses"][:, :, :3, 3] = pi3_result["camera_poses"][:, :, :3, 3] * scale_factor
                 pi3_result["camera_poses_cw"] = torch.linalg.inv(pi3_result["camera_poses"])
 
-            camera_params = None
             if self.config.estimate_camera_params:
                 try:
-                    camera_params = estimate_camera_parameters_single_chunk(pi3_result["local_points"][0],
-                                                                            pi3_result["conf"][0])
+                    pts, val, uv_lr = sample_for_intrinsics(pi3_result["local_points"][0], pi3_result["conf"][0])
+                    pend.intr = (stage(pts), stage(val), uv_lr, int(imgs_dev.shape[-2]), int(imgs_dev.shape[-1]))
                 except Exception as e:
                     print(f"⚠️  Camera parameter estimation failed: {e}")
-                    camera_params = None
-
-            result: Dict = {
-                "camera_poses": pi3_result["camera_poses"][0].cpu(),
-                "image_paths": chunk_paths,
-                "_metrics": _metrics,
-            }
-            if camera_params is not None:
-                result["camera_params"] = {k: v.cpu() for k, v in camera_params.items()}
-            if self.target_size is not None:
-                result["original_width"] = self.target_size[1]
-                result["original_height"] = self.target_size[0]
+            pend.staged["camera_poses"] = stage(pi3_result["camera_poses"][0])
 
             dense = {
                 "points": pi3_result["points"][0].contiguous(),
@@ -232,25 +278,29 @@ class OfflineChunkCreator:
                     kp_res = self.keypoint_extractor.extract(num_frames, H, W)
                     kps = kp_res["keypoints"].to(dev, torch.float32).contiguous()
                     interp = self._interpolate_world_points_for_keypoints(dense, kps)
-                    result["points"] = interp["points"].to(torch.float16).cpu()
-                    result["local_points"] = interp["local_points"].to(torch.float16).cpu()
-                    result["conf"] = interp["conf"].to(torch.float16).cpu()
-                    result["masks"] = interp["masks"].cpu()
-                    result["keypoints"] = kps.to(torch.float16).cpu()
-                    result["descriptors"] = kp_res["descriptors"].to(torch.float16).cpu()
-                    result["scores"] = kp_res["scores"].to(torch.float16).cpu()
-                    result["colors"] = interp["colors"].cpu().to(torch.float16)
+                    pend.staged["points"] = stage(interp["points"].to(torch.float16))
+                    pend.staged["local_points"] = stage(interp["local_points"].to(torch.float16))
+                    pend.staged["conf"] = stage(interp["conf"].to(torch.float16))
+                    pend.staged["masks"] = stage(interp["masks"])
+                    pend.staged["keypoints"] = stage(kps.to(torch.float16))
+                    pend.staged["colors"] = stage(interp["colors"])
+                    pend.staged["descriptors"] = stage(kp_res["descriptors"].to(torch.float16))
+                    pend.staged["scores"] = stage(kp_res["scores"].to(torch.float16))
                     done = True
                 except Exception as e:
                     print(f"⚠️  Keypoint extraction failed: {e}")
             if not done:  # keypoints disabled or failed: dense maps are stored, like the reference
-                result["points"] = dense["points"].cpu()
-                result["local_points"] = dense["local_points"].cpu()
-                result["conf"] = dense["conf"].cpu()
-                result["masks"] = masks.cpu()
-            if result.get("camera_params") is not None:
-                result["intrinsics"] = result["camera_params"].get("intrinsics", None)
-        return result
+                for k in ("points", "local_points", "conf"):
+                    pend.staged.pop(k, None)
+                    pend.host[k] = dense[k].cpu()
+                for k in ("keypoints", "colors", "descriptors", "scores"):
+                    pend.staged.pop(k, None)
+                    pend.host.pop(k, None)
+                pend.staged.pop("masks", None)
+                pend.host["masks"] = masks.cpu()
+            pend.event = torch.cuda.Event()
+            pend.event.record()
+        return pend
 
     @staticmethod
     def _gather_manifest(manifest: List[Dict]) -> List[Dict]:
@@ -301,26 +351,38 @@ class OfflineChunkCreator:
         per_chunk_fps: List[float] = []
         print(f"🔄 Processing {len(mine)} of {len(dataset)} chunks on rank {rank}/{world}...")
         pin = self.config.pin_memory
-        for chunk_idx, ranks in mine:
+
+        def fetch(job: Tuple[int, Tuple[int, ...]]) -> torch.Tensor:
+            """Host frames of one job: the whole chunk, or (sequence-parallel, not the group's first rank) this rank's
+            slice. Runs on the loader threads, `num_loader_workers` chunks ahead of the GPU, like the reference's
+            DataLoader(num_workers, prefetch_factor=1, pin_memory) (:281-289)."""
+            ci, rk = job
+            b, e = dataset.chunk_indices[ci]
+            li = rk.index(rank)
+            if li > 0:
+                n_loc = (e - b) // len(rk)
+                b, e = b + li * n_loc, b + (li + 1) * n_loc
+            # frames of one chunk are decoded by several threads straight into one (pinned) buffer
+            H, W = self.target_size
+            out = torch.empty((e - b, 3, H, W), dtype=torch.float32, pin_memory=pin)
+            step = max(1, -(-(e - b) // frame_threads))
+
+            def part(lo: int) -> None:
+                out[lo - b:min(lo + step, e) - b] = dataset.load_frames(lo, min(lo + step, e))
+            list(frame_pool.map(part, range(b, e, step)))
+            return out
+
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+        depth = max(1, int(self.config.num_loader_workers))
+        frame_threads = max(2, min(8, (os.cpu_count() or 8) // max(1, world)))
+        pool = ThreadPoolExecutor(max_workers=depth)
+        frame_pool = ThreadPoolExecutor(max_workers=frame_threads)
+        pending: deque = deque(pool.submit(fetch, job) for job in mine[:depth])
+        t_wait = t_proc = t_save = 0.0
+
+        def save(chunk_result: Dict, chunk_idx: int, chunk_paths: List) -> None:
             start_idx, end_idx = dataset.chunk_indices[chunk_idx]
-            # default_collate turns the nested path list into 1-tuples (reference Appendix B)
-            chunk_paths = [(p,) for p in dataset.image_paths[start_idx:end_idx]]
-            print(f"📦 Chunk {chunk_idx + 1}/{len(dataset)}: frames {start_idx + 1}-{end_idx}")
-            if self.config.keypoint_seed is not None:
-                torch.manual_seed(self.config.keypoint_seed + chunk_idx)
-            if len(ranks) > 1:
-                def load_frames(a: int, b: int, _s=start_idx) -> torch.Tensor:
-                    t = dataset.load_frames(_s + a, _s + b)
-                    return t.pin_memory() if pin else t
-                chunk_result = self._process_chunk_sequence_parallel(load_frames, end_idx - start_idx, chunk_paths, ranks,
-                                                                     groups[ranks])
-                if chunk_result is None:      # not the group's first rank: nothing to save
-                    continue
-            else:
-                chunk_images = dataset[chunk_idx]["chunk"][None]
-                if pin:
-                    chunk_images = chunk_images.pin_memory()
-                chunk_result = self._process_single_chunk(chunk_images, chunk_paths)
             m = chunk_result.get("_metrics", {})
             if m:
                 infer_times.append(float(m.get("infer_s", 0.0)))
@@ -340,6 +402,65 @@ class OfflineChunkCreator:
             except Exception as e:
                 print(f"❌ Failed to save chunk {chunk_idx}: {e}")
 
+        # Software pipeline over this rank's whole-chunk jobs: the forward of chunk k+1 is enqueued (asynchronously)
+        # before the host half of chunk k (intrinsics LM, dict assembly, torch.save) runs, so the GPU never waits for it.
+        prev: Optional[Tuple[_PendingChunk, int, List]] = None
+
+        def drain() -> None:
+            nonlocal prev, t_save
+            if prev is not None:
+                _t = time.time()
+                pend, ci, cp = prev
+                prev = None
+                save(pend.finish(), ci, cp)
+                t_save += time.time() - _t
+
+        dev = self.config.device
+        for pos, (chunk_idx, ranks) in enumerate(mine):
+            _t = time.time()
+            frames_host = pending.popleft().result()
+            t_wait += time.time() - _t
+            if pos + depth < len(mine):
+                pending.append(pool.submit(fetch, mine[pos + depth]))
+            start_idx, end_idx = dataset.chunk_indices[chunk_idx]
+            # default_collate turns the nested path list into 1-tuples (reference Appendix B)
+            chunk_paths = [(p,) for p in dataset.image_paths[start_idx:end_idx]]
+            print(f"📦 Chunk {chunk_idx + 1}/{len(dataset)}: frames {start_idx + 1}-{end_idx}")
+            _t = time.time()
+            if len(ranks) > 1:
+                drain()
+                if self.config.keypoint_seed is not None:
+                    torch.manual_seed(self.config.keypoint_seed + chunk_idx)
+                chunk_result = self._process_chunk_sequence_parallel(frames_host, end_idx - start_idx, chunk_paths, ranks,
+                                                                     groups[ranks])
+                t_proc += time.time() - _t
+                if chunk_result is not None:      # only the group's first rank saves
+                    _t = time.time()
+                    save(chunk_result, chunk_idx, chunk_paths)
+                    t_save += time.time() - _t
+                continue
+            num_frames = end_idx - start_idx
+            with torch.no_grad():
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                imgs_dev = frames_host[None].to(dev, non_blocking=True)
+                ev0.record()
+                pi3_result = self.model(imgs_dev)
+                ev1.record()
+            t_proc += time.time() - _t
+            drain()                                   # host half of the previous chunk, while this forward runs
+            _t = time.time()
+            if self.config.keypoint_seed is not None:
+                torch.manual_seed(self.config.keypoint_seed + chunk_idx)
+            metrics = {"infer_s": 0.0, "num_frames": int(num_frames), "fps": 0.0}
+            prev = (self._enqueue_finish(pi3_result, imgs_dev, chunk_paths, metrics,
+                                         fwd_events=(time.time(), ev0, ev1, num_frames)), chunk_idx, chunk_paths)
+            t_proc += time.time() - _t
+        drain()
+
+        pool.shutdown(wait=True)
+        frame_pool.shutdown(wait=True)
+        print(f"   host pipeline on rank {rank}: waited {t_wait:.3f}s for frames, {t_proc:.3f}s enqueueing chunks, "
+              f"{t_save:.3f}s in the host half (wait for the GPU, intrinsics solve, save)")
         total_time = sum(infer_times)
         total_frames = sum(infer_frames)
         if total_time > 0:
