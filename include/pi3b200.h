@@ -173,6 +173,16 @@ int pi3b_moge_remap(void* stream, float* points, const float* mask_logit, float*
 int pi3b_moge_depth(void* stream, const float* points, const float* mask_prob, float shift, const float* log_scale,
                     int apply_mask, float* depth, uint8_t* mask_out, int64_t n);
 
+/* Input pipeline: in uint8 [N, Hi, Wi, 3] (decoded RGB frames) -> out fp32 [N, 3, Ho, Wo] in [0,1], bit-identical to
+ * PIL.Image.resize((Wo, Ho), BILINEAR) followed by torchvision ToTensor: Pillow's fixed-point coefficients (22 bits,
+ * caller-built: min index, tap count, int coefficient rows of length ksize per output row / column), horizontal pass
+ * rounded to uint8, then vertical pass, then / 255.
+ * replaces: transforms.Resize(target_size) + ToTensor on the PIL image in the DataLoader workers,
+ *   datasets/image_datasets.py:193-199 and utils/image_utils.py:98-103. */
+int pi3b_resize_u8_pil(void* stream, const uint8_t* in, int N, int Hi, int Wi, float* out, int Ho, int Wo, const int* ymin,
+                       const int* ycnt, const int* ky, int ksize_y, const int* xmin, const int* xcnt, const int* kx,
+                       int ksize_x);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,8 @@ SIGNATURES = {
     "pi3b_moge_remap": (c_int, [_P, _P, _P, _P, c_int, c_int64]),
     # stream, points, mask_prob, shift, log_scale, apply_mask, depth, mask_out, n
     "pi3b_moge_depth": (c_int, [_P, _P, _P, c_float, _P, c_int, _P, _P, c_int64]),
+    # stream, in, N, Hi, Wi, out, Ho, Wo, ymin, ycnt, ky, ksize_y, xmin, xcnt, kx, ksize_x
+    "pi3b_resize_u8_pil": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int]),
 }
 
 

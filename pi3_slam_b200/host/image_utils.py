@@ -46,3 +46,33 @@ def load_image(path: str, target_size: Tuple[int, int]) -> torch.Tensor:
 
 def load_images_from_paths(paths: Sequence[str], target_size: Tuple[int, int]) -> torch.Tensor:
     return torch.stack([load_image(p, target_size) for p in paths])
+
+
+def decode_image_u8(path: str):
+    """PIL decode -> RGB uint8 (H, W, 3) numpy at the source resolution (no resize: that runs on the device)."""
+    from PIL import Image
+    import numpy as np
+    with Image.open(path) as im:
+        return np.asarray(im.convert("RGB"), dtype=np.uint8)
+
+
+def resize_u8_on_host(arr, target_size: Tuple[int, int]) -> torch.Tensor:
+    """Host fallback for frames whose source size differs from the rest of the request: the reference's own
+    PIL resize + ToTensor."""
+    from PIL import Image
+    import numpy as np
+    h, w = target_size
+    im = Image.fromarray(arr)
+    if im.size != (w, h):
+        im = im.resize((w, h), Image.BILINEAR)
+    return torch.from_numpy(np.asarray(im, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255.0)
+
+
+def load_images_u8(paths: Sequence[str], target_size: Tuple[int, int]) -> torch.Tensor:
+    """Decode only: uint8 (N, Hs, Ws, 3) when all frames share one source size (the device then does the Pillow-exact
+    resize + ToTensor, pi3b_resize_u8_pil); otherwise the float (N, 3, H, W) result of the host path."""
+    import numpy as np
+    arrs = [decode_image_u8(p) for p in paths]
+    if all(a.shape == arrs[0].shape for a in arrs):
+        return torch.from_numpy(np.stack(arrs))
+    return torch.stack([resize_u8_on_host(a, target_size) for a in arrs])

@@ -60,3 +60,48 @@ def apply_taps_np(img: np.ndarray, tab_y, tab_x) -> np.ndarray:
     tmp = (img[:, :, xi] * wx[None, None]).sum(-1, dtype=np.float32)          # (C, H, Wo)
     yi = np.minimum(y0[:, None] + np.arange(wy.shape[1])[None], H - 1)
     return (tmp[:, yi, :] * wy[None, :, :, None]).sum(2, dtype=np.float32)     # (C, Ho, Wo)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pillow's 8-bit resampling (what torchvision.transforms.Resize does to a PIL image; reference loader
+# datasets/image_datasets.py:193-199, utils/image_utils.py:98-103). Pillow == 12.x src/libImaging/Resample.c:
+# precompute_coeffs (double), normalize_coeffs_8bpc (fixed point, PRECISION_BITS = 32 - 8 - 2), horizontal pass to a
+# uint8 image, then vertical pass. The tables below are those fixed-point coefficients; pi3b_resize_u8_pil applies
+# them with the same integer arithmetic, so the device result is bit-identical to `Image.resize(size, BILINEAR)`.
+# ---------------------------------------------------------------------------------------------------------------
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_bilinear_coeffs(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(xmin int32 [out], xcount int32 [out], coeffs int32 [out, ksize]) of Pillow's BILINEAR filter (support 1.0)."""
+    scale = filterscale = float(in_size) / float(out_size)
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    xmin_a = np.zeros(out_size, dtype=np.int32)
+    cnt_a = np.zeros(out_size, dtype=np.int32)
+    kk = np.zeros((out_size, ksize), dtype=np.float64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        ww = 0.0
+        for x in range(xmax):
+            a = (x + xmin - center + 0.5) * ss
+            a = -a if a < 0.0 else a
+            w = 1.0 - a if a < 1.0 else 0.0
+            kk[xx, x] = w
+            ww += w
+        if ww != 0.0:
+            for x in range(xmax):       # Pillow divides element by element (not by a reciprocal)
+                kk[xx, x] /= ww
+        xmin_a[xx], cnt_a[xx] = xmin, xmax
+    fixed = np.where(kk < 0, (-0.5 + kk * (1 << PIL_PRECISION_BITS)), (0.5 + kk * (1 << PIL_PRECISION_BITS)))
+    return xmin_a, cnt_a, np.trunc(fixed).astype(np.int32)

@@ -25,7 +25,7 @@ import torch
 from . import _lib, ops
 from .host.camera_estimation import camera_parameters_from_samples, sample_for_intrinsics
 from .host.datasets import ChunkImageDataset, plan_waves
-from .host.image_utils import calculate_target_size
+from .host.image_utils import calculate_target_size, load_images_u8, resize_u8_on_host
 from .host.keypoints import create_keypoint_extractor
 from .pi3 import Pi3
 
@@ -49,6 +49,7 @@ class OfflineCreatorConfig:
     keypoint_seed: Optional[int] = None     # per-chunk re-seeding => sharding-independent keypoints
     moge_model_path: Optional[str] = None   # local MoGe checkpoint (model.pt); None => hub id like the reference
     sequence_parallel_tail: bool = True     # multi-GPU: run the last (partial) wave of chunks sequence-parallel
+    device_resize: bool = True              # loader threads only decode; Pillow-exact resize + ToTensor run on the GPU
 
 
 class _PendingChunk:
@@ -136,6 +137,7 @@ class OfflineChunkCreator:
         self.target_size: Optional[Tuple[int, int]] = None
         self.undistortion_maps = None
         self._sp_groups: Dict[Tuple[int, ...], object] = {}     # rank tuple -> process group of a sequence-parallel wave
+        self._resize_tables: Dict[tuple, tuple] = {}            # (Hs, Ws, H, W) -> Pillow coefficient tables on the device
         if getattr(config, "cam_dist_path", None):
             print("⚠️  cam_dist_path given: undistortion maps (cv2/pytheia) are outside this build; ignoring")
 
@@ -165,6 +167,26 @@ class OfflineChunkCreator:
         p, l, c, m, col = ops.keypoint_gather(dense["points"], dense["local_points"], dense["conf"],
                                               dense["masks"].to(torch.uint8).contiguous(), images, keypoints)
         return {"points": p, "local_points": l, "conf": c, "masks": m, "colors": col}
+
+    def _frames_to_device(self, frames_host: torch.Tensor) -> torch.Tensor:
+        """Host frames -> (1, N, 3, H, W) fp32 on the device. float frames (already at the target size) are copied;
+        uint8 (N, Hs, Ws, 3) decoded frames are copied as bytes and resized + converted by pi3b_resize_u8_pil,
+        bit-identical to the reference's PIL Resize + ToTensor (datasets/image_datasets.py:193-199)."""
+        dev = self.config.device
+        if frames_host.dtype != torch.uint8:
+            return frames_host[None].to(dev, non_blocking=True)
+        from .host.resample import pil_bilinear_coeffs
+        n, hs, ws, _ = frames_host.shape
+        H, W = self.target_size
+        key = (hs, ws, H, W)
+        tabs = self._resize_tables.get(key)
+        if tabs is None:
+            tabs = tuple(tuple(torch.from_numpy(a).to(dev).contiguous() for a in pil_bilinear_coeffs(i, o))
+                         for i, o in ((hs, H), (ws, W)))
+            self._resize_tables[key] = tabs
+        out = torch.empty(n, 3, H, W, device=dev, dtype=torch.float32)
+        ops.resize_u8_pil(frames_host.to(dev, non_blocking=True), out, tabs[0], tabs[1])
+        return out[None]
 
     # ------------------------------------------------------------------ one chunk
     def _process_single_chunk(self, chunk_images: torch.Tensor, chunk_paths: List[str]) -> Dict:
@@ -204,11 +226,11 @@ class OfflineChunkCreator:
         with torch.no_grad():
             t0 = time.time()
             if leader:
-                imgs_dev = frames_host[None].to(dev, non_blocking=True)
+                imgs_dev = self._frames_to_device(frames_host)
                 local = imgs_dev[:, :n_loc]
             else:
                 imgs_dev = None
-                local = frames_host[None].to(dev, non_blocking=True)
+                local = self._frames_to_device(frames_host)
             out = self.model(local.contiguous(), sp_group=group)
             full = {}
             for k in ("points", "local_points", "conf", "camera_poses"):
@@ -327,6 +349,8 @@ class OfflineChunkCreator:
         self.target_size = target_size or calculate_target_size(image_paths[0], pixel_limit=255000 // 2)
         print(f"Target size: {self.target_size}")
 
+        if loader is None and self.config.device_resize:
+            loader = load_images_u8
         dataset = ChunkImageDataset(image_paths, self.config.chunk_length, self.config.overlap, self.target_size,
                                     device="cpu", loader=loader)
         rank, world = 0, 1
@@ -362,14 +386,15 @@ class OfflineChunkCreator:
             if li > 0:
                 n_loc = (e - b) // len(rk)
                 b, e = b + li * n_loc, b + (li + 1) * n_loc
-            # frames of one chunk are decoded by several threads straight into one (pinned) buffer
-            H, W = self.target_size
-            out = torch.empty((e - b, 3, H, W), dtype=torch.float32, pin_memory=pin)
+            # frames of one chunk are decoded by several threads, then gathered into one (pinned) buffer
             step = max(1, -(-(e - b) // frame_threads))
-
-            def part(lo: int) -> None:
-                out[lo - b:min(lo + step, e) - b] = dataset.load_frames(lo, min(lo + step, e))
-            list(frame_pool.map(part, range(b, e, step)))
+            parts = list(frame_pool.map(lambda lo: dataset.load_frames(lo, min(lo + step, e)), range(b, e, step)))
+            if any(p.dtype != parts[0].dtype or p.shape[1:] != parts[0].shape[1:] for p in parts):
+                # mixed source sizes: finish those frames with the reference's host resize
+                parts = [p if p.dtype == torch.float32 else
+                         torch.stack([resize_u8_on_host(f.numpy(), self.target_size) for f in p]) for p in parts]
+            out = torch.empty((e - b,) + tuple(parts[0].shape[1:]), dtype=parts[0].dtype, pin_memory=pin)
+            torch.cat(parts, out=out)
             return out
 
         from collections import deque
@@ -442,7 +467,7 @@ class OfflineChunkCreator:
             num_frames = end_idx - start_idx
             with torch.no_grad():
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                imgs_dev = frames_host[None].to(dev, non_blocking=True)
+                imgs_dev = self._frames_to_device(frames_host)
                 ev0.record()
                 pi3_result = self.model(imgs_dev)
                 ev1.record()

@@ -396,3 +396,24 @@ def moge_depth(points: torch.Tensor, mask_prob: Optional[torch.Tensor], shift: f
                              1 if apply_mask else 0, depth.data_ptr(), mask.data_ptr(), n)
     _lib.check(rc, "pi3b_moge_depth")
     return depth, mask
+
+
+def resize_u8_pil(frames_u8: torch.Tensor, out: torch.Tensor, tab_y, tab_x) -> torch.Tensor:
+    """uint8 [N,Hi,Wi,3] -> fp32 [N,3,Ho,Wo] in [0,1], bit-identical to PIL BILINEAR resize + ToTensor.
+    tab_* = (min int32 [out], count int32 [out], coeffs int32 [out, ksize]) on the device
+    (host.resample.pil_bilinear_coeffs)."""
+    lib = _lib.load()
+    _req(frames_u8, torch.uint8, "frames_u8"); _req(out, torch.float32, "out")
+    assert frames_u8.is_contiguous() and out.is_contiguous() and frames_u8.dim() == 4 and frames_u8.shape[3] == 3
+    N, Hi, Wi, _ = frames_u8.shape
+    assert out.shape[0] == N and out.shape[1] == 3
+    Ho, Wo = out.shape[2:]
+    (ymin, ycnt, ky), (xmin, xcnt, kx) = tab_y, tab_x
+    for t in (ymin, ycnt, ky, xmin, xcnt, kx):
+        assert t.dtype == torch.int32 and t.is_cuda and t.is_contiguous()
+    assert ymin.numel() == Ho and xmin.numel() == Wo and ky.shape[0] == Ho and kx.shape[0] == Wo
+    rc = lib.pi3b_resize_u8_pil(_stream(), frames_u8.data_ptr(), N, Hi, Wi, out.data_ptr(), Ho, Wo, ymin.data_ptr(),
+                                ycnt.data_ptr(), ky.data_ptr(), ky.shape[1], xmin.data_ptr(), xcnt.data_ptr(),
+                                kx.data_ptr(), kx.shape[1])
+    _lib.check(rc, "pi3b_resize_u8_pil")
+    return out

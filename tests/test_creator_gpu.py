@@ -237,3 +237,48 @@ def test_metric_scale_branch_with_injected_depth_model(model, tmp_path):
     assert torch.allclose(out["points"], ref["points"] * s, rtol=1e-6)
     assert torch.allclose(out["camera_poses"][:, :3, 3], ref["camera_poses"][:, :3, 3] * s, rtol=1e-6)
     assert torch.equal(out["camera_poses"][:, :3, :3], ref["camera_poses"][:, :3, :3])
+
+
+@pytest.mark.parametrize("shape", [(480, 640, 308, 406), (224, 224, 350, 364), (100, 60, 37, 91), (126, 98, 126, 98)])
+def test_device_resize_is_bit_exact_vs_pillow(shape):
+    """pi3b_resize_u8_pil == PIL.Image.resize(BILINEAR) + ToTensor, bit for bit (integer work)."""
+    from PIL import Image
+    import torchvision.transforms as T
+    from pi3_slam_b200 import ops
+    from pi3_slam_b200.host.resample import pil_bilinear_coeffs
+    hi, wi, ho, wo = shape
+    rng = np.random.default_rng(hi + wo)
+    frames = rng.integers(0, 256, (3, hi, wi, 3), dtype=np.uint8)
+    tf = T.Compose([T.Resize((ho, wo)), T.ToTensor()])
+    ref = torch.stack([tf(Image.fromarray(f)) for f in frames])
+    tabs = tuple(tuple(torch.from_numpy(a).cuda().contiguous() for a in pil_bilinear_coeffs(i, o)) for i, o in ((hi, ho), (wi, wo)))
+    out = ops.resize_u8_pil(torch.from_numpy(frames).cuda(), torch.empty(3, 3, ho, wo, device="cuda"), tabs[0], tabs[1])
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_process_and_save_from_png_files_device_resize_equals_host_resize(model, tmp_path):
+    """Real files through the whole stage: PNG decode on loader threads, then either the reference's host-side PIL
+    resize (device_resize=False) or the device kernel — the chunk files must be identical bit for bit."""
+    from PIL import Image
+    from pi3_slam_b200.offline_chunk_creator import OfflineChunkCreator, OfflineCreatorConfig
+    rng = np.random.default_rng(5)
+    paths = []
+    base = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    for i in range(7):
+        p = str(tmp_path / f"frame_{i:04d}.png")
+        Image.fromarray(np.roll(base, 5 * i, axis=1)).save(p)
+        paths.append(p)
+    outs = {}
+    for mode in (True, False):
+        cfg = OfflineCreatorConfig(model_path="unused", output_dir=str(tmp_path / f"dev{int(mode)}"), device="cuda",
+                                   do_metric_depth=False, keypoint_type="grid", max_num_keypoints=40, chunk_length=4,
+                                   overlap=1, keypoint_seed=3, device_resize=mode)
+        cr = OfflineChunkCreator(cfg, model=model)
+        files = cr.process_and_save(paths)
+        assert cr.target_size[0] % 14 == 0 and cr.target_size[1] % 14 == 0
+        outs[mode] = [torch.load(f, weights_only=False) for f in files]
+    assert len(outs[True]) == len(outs[False]) == 2
+    for a, b in zip(outs[True], outs[False]):
+        for k in ("points", "local_points", "conf", "masks", "camera_poses", "keypoints", "colors", "intrinsics"):
+            assert torch.equal(a[k], b[k]), k
+        assert a["image_paths"] == b["image_paths"]

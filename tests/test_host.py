@@ -3,6 +3,7 @@ import json
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -143,3 +144,39 @@ def test_from_pretrained_reads_reference_style_directory(tmp_path):
     for k in ("decoder.35.mlp.fc2.weight", "camera_head.fc_rot.bias", "encoder.pos_embed", "image_std"):
         assert torch.equal(got[k], sd[k]), k
     assert m.rope_freq == 100.0
+
+
+@pytest.mark.parametrize("shape", [(480, 640, 308, 406), (480, 752, 280, 448), (224, 224, 350, 364), (100, 60, 37, 91),
+                                   (50, 50, 50, 20), (126, 98, 126, 98)])
+def test_pil_resize_oracle_is_bit_exact_vs_pillow(shape):
+    """The restated integer algorithm (and the coefficient tables the device kernel consumes) against Pillow itself —
+    the library the reference's loader calls (datasets/image_datasets.py:193-199)."""
+    from PIL import Image
+    from oracle.pil_resize_oracle import pil_resize_bilinear_u8, to_tensor
+    from pi3_slam_b200.host.resample import pil_bilinear_coeffs
+    import torchvision.transforms as T
+    hi, wi, ho, wo = shape
+    rng = np.random.default_rng(hi * 7 + wo)
+    img = rng.integers(0, 256, (hi, wi, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((wo, ho), Image.BILINEAR))
+    got = pil_resize_bilinear_u8(img, ho, wo, pil_bilinear_coeffs(hi, ho), pil_bilinear_coeffs(wi, wo))
+    assert np.array_equal(ref, got)
+    # and the full reference transform: Resize((H, W)) + ToTensor on the PIL image
+    ref_t = T.Compose([T.Resize((ho, wo)), T.ToTensor()])(Image.fromarray(img)).numpy()
+    assert np.array_equal(ref_t, to_tensor(got))
+
+
+def test_load_images_u8_and_mixed_size_fallback(tmp_path):
+    from PIL import Image
+    from pi3_slam_b200.host.image_utils import load_images_from_paths, load_images_u8
+    rng = np.random.default_rng(1)
+    paths = []
+    for i, (h, w) in enumerate([(60, 80), (60, 80), (48, 64)]):
+        p = str(tmp_path / f"f{i}.png")
+        Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(p)
+        paths.append(p)
+    same = load_images_u8(paths[:2], (28, 42))
+    assert same.dtype == torch.uint8 and same.shape == (2, 60, 80, 3)
+    mixed = load_images_u8(paths, (28, 42))
+    assert mixed.dtype == torch.float32 and mixed.shape == (3, 3, 28, 42)
+    assert torch.equal(mixed, load_images_from_paths(paths, (28, 42)))
