@@ -117,6 +117,17 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: until it is emitted fd 1 points at stderr, so native writers (the NCCL
+    # version banner is a printf to stdout, whatever NCCL_DEBUG_FILE says) cannot interleave with it
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj) -> None:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(obj), flush=True)
+
     frames, H, W, desc = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -138,7 +149,7 @@ def main():
                 "config": config, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     import torch
@@ -258,7 +269,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(CPU_SAMPLE_FRAMES, H, W, 1, 0, sd)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
