@@ -32,7 +32,12 @@
 // consumers lagging one block behind the exponentials (ptxas re-interleaves them, also across bar.warp.sync), 64-column
 // steps with double / triple buffered S, intra-warp S prefetch, strict MUFU ping-pong via named barriers. Without any
 // exponentials the kernel reaches 1000 TFLOP/s, so the remaining gap to the tensor roofline is synchronisation latency,
-// not MUFU throughput or TMEM bandwidth.
+// not MUFU throughput or TMEM bandwidth. The two tiles do NOT run in lockstep: QK0(0) / QK1(0) are issued back to back,
+// which leaves tile 1 about 1000 clocks (a third of a step) behind tile 0 for the whole kernel, and an extra start delay
+// of 500 / 900 / 1400 clocks for tile 1 changes nothing (845-853 TFLOP/s, profiles/r01_attn_stagger_ab.log): the
+// ~1650-clock exponential phase is the warp's own in-order stream (~550 instructions, each MUFU pair consumed ~6
+// instructions later), not contention between the two groups. What would hide it is more resident softmax warps per
+// scheduler (4 Q tiles x 64-column steps with P aliased onto S fit TMEM exactly: 4 x (64 + 64) columns) — next round.
 #include "host_common.h"
 #include "ptx.cuh"
 
