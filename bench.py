@@ -93,6 +93,14 @@ def cpu_reference_run(frames: int, H: int, W: int, steps: int, warmup: int, sd=N
     import torch
     from oracle import pi3_oracle
     from pi3_slam_b200.synthetic import make_frames, make_state_dict
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently turn the CPU arm into a single-core run
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    if torch.get_num_threads() < ncores:
+        torch.set_num_threads(ncores)
     sd = sd if sd is not None else make_state_dict(0)
     imgs = make_frames(frames, H, W)[None]
     for _ in range(warmup):
