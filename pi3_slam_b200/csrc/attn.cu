@@ -448,8 +448,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // pipe and the kernel fell to 645 TFLOP/s; decoupled, the tiles drift apart and it reaches 880-890 (revision 5 on the
 // same box: 855-868), profiles/r01_attn_rev8_ab.log. ptxas sizes each role's code to its setmaxnreg budget, and the
 // budgets must add up to the CTA's launch allocation (threads x launch registers) or the last setmaxnreg.inc blocks
-// forever. Tried on top and not kept: four tiles with P written in place over S (correct — the in-order tensor pipe lets
-// QK(j+1) overwrite P(j) right behind PV(j) — but at 640 threads the softmax loop spills 2 KB/thread and it ran 14x slower).
+// forever. The four-tile layout (P in place over S) is revision 9 below; its first form (single-pass softmax spilling
+// 2 KB/thread at 640 threads, issuer warps spinning on two tiles each) ran 14x slower.
 // =====================================================================================================================
 constexpr int kA3Threads = 512;
 constexpr int kA3Tiles = 3;
@@ -735,6 +735,302 @@ attn_fwd_kernel_t3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 
+// =====================================================================================================================
+// Revision 9 (default for kv_len <= 8192): FOUR 128-row Q tiles per CTA, 64-column KV steps, P written in place over
+// the first 32 columns of its own S tile (S/P 4 x 64 + O 4 x 64 = 512 TMEM columns), four softmax warps per scheduler.
+// Two issuer warps serve two tiles each, in a fixed order with per-tile blocking waits: PV(j) and then QK(j+1) back to
+// back (the tensor pipe executes them in order, so the new scores overwrite P only after PV has read it); no s_free /
+// per-step pv_done handshakes remain on the softmax side. The softmax step is two passes over 32-column halves (row max,
+// then exponentials, S re-read from TMEM) so that it fits the 96 registers a 640-thread CTA leaves per thread.
+// =====================================================================================================================
+constexpr int kA4Tiles = 4;
+constexpr int kA4Threads = 32 * (4 + 4 * kA4Tiles);   // warp 0 TMA, warps 1-2 issuers (2 tiles each), warps 4-19 softmax
+constexpr int kA4Stages = 8;
+struct Attn4Smem {
+  static constexpr int Q_OFF = 0;
+  static constexpr int K_OFF = kA4Tiles * kTileBytes;
+  static constexpr int V_OFF = K_OFF + kA4Stages * kA3KvBytes;
+  static constexpr int BAR_OFF = V_OFF + kA4Stages * kA3KvBytes;
+  static constexpr int NUM_BARS = 1 + 3 * kA4Stages + 3 * kA4Tiles;
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
+};
+constexpr uint32_t kT4S = 0;     // S tile t at t*64 (64 fp32 columns); P tile t = its first 32 columns (64 packed bf16)
+constexpr uint32_t kT4O = 256;   // O tile t at 256 + t*64
+
+__global__ void __launch_bounds__(kA4Threads, 1)
+attn_fwd_kernel_t4(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Attn4Smem::BAR_OFF);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = k_full + kA4Stages;
+  uint64_t* kv_empty = v_full + kA4Stages;
+  uint64_t* s_full = kv_empty + kA4Stages;
+  uint64_t* p_full = s_full + kA4Tiles;
+  uint64_t* pv_done = p_full + kA4Tiles;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + kA4Tiles);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  constexpr int kRows = 128 * kA4Tiles;
+  const int num_qblocks = (p.q_len + kRows - 1) / kRows;
+  int item = blockIdx.x;
+  const int qb = item % num_qblocks;
+  item /= num_qblocks;
+  const int seq = item % p.num_seqs;
+  const int head = item / p.num_seqs;
+  const int row_base = seq * p.q_len;
+  const int kv_base = seq * p.kv_len;
+  const int q0 = qb * kRows;
+  const int q_valid = min(kRows, p.q_len - q0);
+  const int num_t = (q_valid + 127) / 128;
+  const int num_kv = (p.kv_len + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kA4Stages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], num_t);   // one tcgen05.commit per tile issuer
+    }
+    for (int t = 0; t < kA4Tiles; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&pv_done[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      mbar_expect_tx(q_full, num_t * kTileBytes);
+      for (int t = 0; t < num_t; ++t)
+        tma_load_2d(smem + Attn4Smem::Q_OFF + t * kTileBytes, &tmQ, q_full, p.q_col0 + head * 64,
+                    row_base + q0 + t * 128, kEvictFirst);
+    }
+    __syncwarp();
+    for (int j = 0; j < num_kv; ++j) {
+      const int s = j % kA4Stages;
+      const uint32_t ph = (j / kA4Stages) & 1;
+      mbar_wait(&kv_empty[s], ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&k_full[s], kA3KvBytes);
+        tma_load_2d(smem + Attn4Smem::K_OFF + s * kA3KvBytes, &tmK, &k_full[s], p.k_col0 + head * 64,
+                    kv_base + j * 64, kEvictLast);
+        mbar_expect_tx(&v_full[s], kA3KvBytes);
+        tma_load_2d(smem + Attn4Smem::V_OFF + s * kA3KvBytes, &tmV, &v_full[s], p.v_col0 + head * 64,
+                    kv_base + j * 64, kEvictLast);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 3) {
+    // ===== MMA issuers: warp 1 serves tiles 0,1 and warp 2 tiles 2,3, each in a fixed order with per-tile waits =====
+    constexpr uint32_t idesc_qk = make_idesc(1, 128, 64, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc(1, 128, 64, 0, 1);  // B (=V) is MN-major
+    const uint64_t k_desc = make_smem_desc_sw128(smem_u32(smem + Attn4Smem::K_OFF), 16, 1024);
+    const uint64_t v_desc = make_smem_desc_sw128(smem_u32(smem + Attn4Smem::V_OFF), 1024, 1024);
+    const int t0 = (warp - 1) * 2;
+    const int n_mine = min(2, num_t - t0);          // tiles this warp serves (<= 0: none)
+    if (n_mine > 0) {
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int i = 0; i < n_mine; ++i) {
+        const int t = t0 + i;
+        const uint64_t q_desc = make_smem_desc_sw128(smem_u32(smem + Attn4Smem::Q_OFF + t * kTileBytes), 16, 1024);
+        const uint32_t d_s = tmem_base + kT4S + t * 64;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(d_s, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
+          umma_commit(&s_full[t]);
+        }
+        __syncwarp();
+      }
+      for (int j = 0; j < num_kv; ++j) {
+        const int s = j % kA4Stages;
+        const int sn = (j + 1) % kA4Stages;
+        const bool more = j + 1 < num_kv;
+        mbar_wait(&v_full[s], (j / kA4Stages) & 1);
+        if (more) mbar_wait(&k_full[sn], ((j + 1) / kA4Stages) & 1);
+        const uint64_t vb = v_desc + uint64_t((s * kA3KvBytes) >> 4);
+        const uint64_t kb = k_desc + uint64_t((sn * kA3KvBytes) >> 4);
+        for (int i = 0; i < n_mine; ++i) {
+          const int t = t0 + i;
+          mbar_wait(&p_full[t], j & 1);     // P_t(j) is in TMEM (over S_t(j), which is fully consumed)
+          tc_fence_after();
+          const uint64_t q_desc = make_smem_desc_sw128(smem_u32(smem + Attn4Smem::Q_OFF + t * kTileBytes), 16, 1024);
+          const uint32_t d_s = tmem_base + kT4S + t * 64;   // S_t, and P_t in its first 32 columns
+          const uint32_t d_o = tmem_base + kT4O + t * 64;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ts(d_o, d_s + k * 8, vb + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0);
+            umma_commit(&pv_done[t]);
+            if (more) {
+              // in-order tensor pipe: these writes to S_t follow PV(j)'s reads of P_t
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16_ss(d_s, q_desc + 2 * k, kb + 2 * k, idesc_qk, k != 0);
+              umma_commit(&s_full[t]);
+            }
+            umma_commit(&kv_empty[s]);     // this tile's QK(j) and PV(j) have consumed stage s
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // idle
+  } else {
+    // ===== softmax groups: one thread per query row, 64 columns per step =====
+    const int t = (warp - 4) >> 2;
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    if (t < num_t) {
+      const uint32_t lane_sel = uint32_t(quarter * 32) << 16;
+      const uint32_t tm_s = tmem_base + lane_sel + kT4S + t * 64;
+      const uint32_t tm_o = tmem_base + lane_sel + kT4O + t * 64;
+      const int row_in_cta = t * 128 + quarter * 32 + lane;
+      const float sc = p.scale_log2;
+      float m_used = -INFINITY;
+      const uint64_t sc2 = pack2(sc, sc);
+      uint64_t lsum = pack2(0.f, 0.f);
+      for (int j = 0; j < num_kv; ++j) {
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        const int kv_valid = p.kv_len - j * 64;
+        // pass 1: row max (both halves in flight at once: only the max chains are live next to the 64 scores)
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        {
+          uint32_t a[64];
+          tmem_ld_x32(tm_s, a);
+          tmem_ld_x32(tm_s + 32, a + 32);
+          tmem_ld_wait();
+          if (kv_valid < 64) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (c >= kv_valid) a[c] = 0xff800000u;  // -inf
+          }
+#pragma unroll
+          for (int c = 0; c < 64; c += 8) {
+            mx0 = max3(mx0, __uint_as_float(a[c]), __uint_as_float(a[c + 1]));
+            mx1 = max3(mx1, __uint_as_float(a[c + 2]), __uint_as_float(a[c + 3]));
+            mx2 = max3(mx2, __uint_as_float(a[c + 4]), __uint_as_float(a[c + 5]));
+            mx3 = max3(mx3, __uint_as_float(a[c + 6]), __uint_as_float(a[c + 7]));
+          }
+        }
+        const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+
+        if (j == 0) {
+          m_used = m_tile;
+        } else {
+          const bool grow = m_tile > m_used + 8.0f;
+          if (__any_sync(0xffffffffu, grow)) {
+            // O_t must be quiescent: PV(j-1) has finished (S(j) being ready already implies it: QK(j) was issued behind
+            // PV(j-1) on the in-order pipe; the wait makes the dependency explicit)
+            mbar_wait(&pv_done[t], (j - 1) & 1);
+            tc_fence_after();
+            float alpha = 1.0f;
+            if (grow) {
+              alpha = fast_exp2(m_used - m_tile);
+              m_used = m_tile;
+            }
+            float la, lb;
+            unpack2(lsum, la, lb);
+            lsum = pack2(la * alpha, lb * alpha);
+            uint32_t o[32];
+#pragma unroll
+            for (int hcol = 0; hcol < 64; hcol += 32) {
+              tmem_ld_x32(tm_o + hcol, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              tmem_st_x32(tm_o + hcol, o);
+            }
+            tmem_st_wait();
+          }
+        }
+
+        const uint64_t negm2 = pack2(-m_used, -m_used);
+        // pass 2: exponentials; S is re-read from TMEM, P (packed bf16) goes over the first 32 columns of S
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t a[32];
+          tmem_ld_x32(tm_s + h * 32, a);
+          tmem_ld_wait();
+          if (kv_valid < 64) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (h * 32 + c >= kv_valid) a[c] = 0xff800000u;  // -inf
+          }
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const uint64_t x = ffma2(pack2(__uint_as_float(a[c]), __uint_as_float(a[c + 1])), sc2, negm2);
+            float x0, x1;
+            unpack2(x, x0, x1);
+            const float p0 = (kPolyEvery > 0 && (c % (2 * (kPolyEvery > 0 ? kPolyEvery : 1))) == 0) ? poly_exp2(x0) : fast_exp2(x0);
+            const float p1 = fast_exp2(x1);
+            lsum = fadd2(lsum, pack2(p0, p1));
+            a[c >> 1] = pack_bf16x2(p0, p1);
+          }
+          // P half h goes to columns [16h, 16h+16); the other half's scores (columns 32..63) are still intact
+          tmem_st_x16(tm_s + h * 16, a);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+
+      mbar_wait(&pv_done[t], (num_kv - 1) & 1);
+      tc_fence_after();
+      float la, lb;
+      unpack2(lsum, la, lb);
+      const float inv_l = 1.0f / (la + lb);
+      const bool row_ok = row_in_cta < q_valid;
+      __nv_bfloat16* orow = p.out + size_t(row_base + q0 + row_in_cta) * p.ldo + head * 64;
+#pragma unroll
+      for (int hcol = 0; hcol < 64; hcol += 32) {
+        uint32_t o[32];
+        tmem_ld_x32(tm_o + hcol, o);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+            v.y = pack_bf16x2(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+            v.z = pack_bf16x2(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+            v.w = pack_bf16x2(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + hcol + c) = v;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace pi3b
 
 using namespace pi3b;
@@ -757,16 +1053,23 @@ extern "C" int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, co
   const uint64_t rows = uint64_t(num_seqs) * q_len;
   const uint64_t kv_rows = uint64_t(num_seqs) * kv_len;
   PI3B_REQUIRE(rows < (1ull << 31) && kv_rows < (1ull << 31), "pi3b_attn_fwd_hd64: too many rows");
-  // revision 8 (3 Q tiles x 64-column steps) is the default; PI3B_ATTN_REV=5 selects revision 5 (2 tiles x 128) for A/B runs
-  static const int rev = []() { const char* e = getenv("PI3B_ATTN_REV"); return (e && atoi(e) == 5) ? 5 : 8; }();
-  const int rows_per_cta = rev == 8 ? 384 : 256;
+  // Default: revision 9 (four tiles) for short sequences — frame-local attention, +9 % at S = 1004 — and revision 8
+  // (three tiles) for long ones (chunk-global attention, +1.5 % at S = 100400); same-box A/B in
+  // profiles/r01_attn_rev8_ab.log. PI3B_ATTN_REV=5|8|9 forces one kernel (A/B runs).
+  static const int forced = []() {
+    const char* e = getenv("PI3B_ATTN_REV");
+    const int r = e ? atoi(e) : 0;
+    return (r == 5 || r == 8 || r == 9) ? r : 0;
+  }();
+  const int rev = forced ? forced : (kv_len <= 8192 ? 9 : 8);
+  const int rows_per_cta = rev == 9 ? 512 : (rev == 8 ? 384 : 256);
   const int64_t items = int64_t((q_len + rows_per_cta - 1) / rows_per_cta) * num_seqs * num_heads;
   PI3B_REQUIRE(items < (1ll << 31), "pi3b_attn_fwd_hd64: too many work items");
 
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   if ((rc = make_tmap_2d(&tmQ, q, 0, rows, uint64_t(q_col0) + 64ull * num_heads, uint64_t(ldq) * 2, 128, 64))) return rc;
-  const uint32_t kv_box = rev == 8 ? 64 : 128;
+  const uint32_t kv_box = rev >= 8 ? 64 : 128;
   if ((rc = make_tmap_2d(&tmK, k, 0, kv_rows, uint64_t(k_col0) + 64ull * num_heads, uint64_t(ldk) * 2, kv_box, 64))) return rc;
   if ((rc = make_tmap_2d(&tmV, v, 0, kv_rows, uint64_t(v_col0) + 64ull * num_heads, uint64_t(ldv) * 2, kv_box, 64))) return rc;
 
@@ -778,6 +1081,9 @@ extern "C" int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, co
     if (cudaFuncSetAttribute(attn_fwd_kernel_t3, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL) !=
         cudaSuccess)
       return check_launch("attn: cudaFuncSetAttribute (t3)");
+    if (cudaFuncSetAttribute(attn_fwd_kernel_t4, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL) !=
+        cudaSuccess)
+      return check_launch("attn: cudaFuncSetAttribute (t4)");
     configured = true;
   }
   AttnParams p;
@@ -786,7 +1092,9 @@ extern "C" int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, co
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = (int)ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
-  if (rev == 8)
+  if (rev == 9)
+    attn_fwd_kernel_t4<<<(unsigned)items, kA4Threads, Attn4Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  else if (rev == 8)
     attn_fwd_kernel_t3<<<(unsigned)items, kA3Threads, Attn3Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   else
     attn_fwd_kernel<<<(unsigned)items, kAttnThreads, AttnSmem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);

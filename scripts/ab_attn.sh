@@ -2,7 +2,7 @@
 # A/B the attention kernel variants built under pi3_slam_b200/build/variants (same process conditions, same box)
 mkdir -p gpurun_out
 cd scripts
-for rep in 1 2; do
+for rep in ${REPS:-1 2}; do
 for v in ../pi3_slam_b200/build/variants/*.so; do
   echo "== $v (rep $rep)"
   PI3B_LIB=$(realpath $v) timeout -s KILL 100 python -c "
