@@ -180,3 +180,28 @@ def test_load_images_u8_and_mixed_size_fallback(tmp_path):
     mixed = load_images_u8(paths, (28, 42))
     assert mixed.dtype == torch.float32 and mixed.shape == (3, 3, 28, 42)
     assert torch.equal(mixed, load_images_from_paths(paths, (28, 42)))
+
+
+def test_camera_parameters_from_samples_matches_oracle():
+    """Host half of the intrinsics estimate (scipy LM per frame + focal -> K formulas) against the oracle restatement of
+    utils/camera_estimation.py on 64x64 maps, where the nearest down-sampling is the identity."""
+    from oracle import chunk_oracle as co
+    from pi3_slam_b200.host.camera_estimation import (camera_parameters_from_samples, nearest_indices,
+                                                      normalized_view_plane_uv)
+    g = torch.Generator().manual_seed(0)
+    N, H, W = 3, 64, 64
+    uv = torch.from_numpy(normalized_view_plane_uv(W, H))
+    z = 1.5 + torch.rand(N, H, W, generator=g)
+    xy = uv[None] * (z[..., None] + 0.3) / 1.1 + 0.01 * torch.randn(N, H, W, 2, generator=g)   # focal 1.1, shift 0.3
+    local_points = torch.cat([xy, z[..., None]], dim=-1).float()
+    conf = torch.randn(N, H, W, 1, generator=g) * 2
+    ref = co.camera_params(local_points, conf)
+    ys, xs = nearest_indices(H, 64), nearest_indices(W, 64)
+    assert list(ys) == list(range(64)) and list(xs) == list(range(64))
+    valid = (torch.sigmoid(conf[..., 0]) > 0.1).reshape(N, -1).numpy()
+    got = camera_parameters_from_samples(local_points.reshape(N, -1, 3).numpy(), valid, uv.reshape(-1, 2).numpy(), H, W)
+    assert set(got) == set(ref)
+    for k in ref:
+        assert got[k].shape == ref[k].shape, k
+        assert torch.allclose(got[k], ref[k], rtol=1e-5, atol=1e-6), k
+    assert abs(float(got["focal"][0, 0]) - 1.1) < 0.05 and abs(float(got["shift"][0, 0]) - 0.3) < 0.1
