@@ -13,8 +13,10 @@ def _ref(qkv, B, S, H):
 
 # (num_seqs, seq_len, heads): frame-local shapes (T=261, 643, 1004), multiples of the tile sizes, ragged
 # tails on both the Q and the KV side, and a chunk-global shape.
+# Sequences up to 8192 keys run the four-tile kernel (revision 9), longer ones the three-tile kernel (revision 8): both
+# sides of the dispatch are covered, and test_every_revision_when_forced pins each kernel on both kinds of shape.
 CASES = [(1, 128, 1), (1, 256, 2), (2, 384, 2), (3, 261, 16), (2, 643, 4), (2, 1004, 16), (1, 5, 1), (1, 129, 2),
-         (1, 8 * 261, 16), (1, 4099, 3)]
+         (1, 8 * 261, 16), (1, 4099, 3), (1, 9001, 2), (1, 8193, 1)]
 
 
 @pytest.mark.parametrize("B,S,H", CASES)
@@ -67,3 +69,34 @@ def test_attention_local_queries_against_longer_kv():
         ops.attention_q_kv(qkv[lo:hi], kv, out, 1, hi - lo, S, H)
         err = (out.float() - ref[lo:hi]).norm() / ref[lo:hi].norm()
         assert err.item() < 1e-2, f"rows {lo}:{hi} rel err {err.item():.3e}"
+
+
+@pytest.mark.parametrize("rev", [5, 8, 9])
+def test_every_revision_when_forced(rev):
+    """PI3B_ATTN_REV pins one kernel for every shape (the library reads it once per process, hence the subprocess):
+    each revision must be correct on short ragged sequences and on a long one, whatever the default dispatch picks."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from pi3_slam_b200 import ops
+worst = 0.0
+for (B, S, H) in [(2, 643, 4), (1, 129, 2), (1, 8700, 1)]:
+    torch.manual_seed(S)
+    qkv = torch.randn(B * S, 3 * H * 64, device="cuda").bfloat16()
+    out = torch.full((B * S, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attention_qkv(qkv, out, B, S, H)
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * S, H * 64)
+    assert torch.isfinite(out.float()).all()
+    worst = max(worst, float((out.float() - ref).norm() / ref.norm()))
+print("WORST", worst)
+""" % root
+    env = dict(os.environ, PI3B_ATTN_REV=str(rev))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split("WORST")[-1])
+    assert worst < 1e-2, f"revision {rev}: rel err {worst:.3e}"
