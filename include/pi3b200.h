@@ -9,7 +9,8 @@
  *   - matrices are row-major with unit inner stride; `ld*` are row pitches in ELEMENTS.
  *   - return value: 0 = ok; -1 bad argument; -2 CUDA launch/runtime error; -3 driver (TMA descriptor) error.
  *     pi3b_last_error() returns a thread-local message for the last failing call on this thread.
- *   - thread-safe for concurrent calls on distinct streams.
+ *   - thread-safe for concurrent calls on distinct streams and on distinct devices (per-device function attributes and
+ *     SM counts; the caller makes the tensors' device current before the call, as the CUDA runtime requires).
  *
  * "replaces:" cites the reference interface (file:line in urbste/Pi3_SLAM) each entry point stands in for.
  */
@@ -46,6 +47,23 @@ int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda, const void
 int pi3b_attn_fwd_hd64(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
                        int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo, int num_seqs,
                        int q_len, int kv_len, int num_heads, float scale);
+
+/* Same, and additionally lse[h * num_seqs*q_len + row] = max_j(x_j) + log2(sum_j 2^(x_j - max)) with
+ * x_j = (q . k_j) * scale * log2(e): the log2-domain log-sum-exp of the row, fp32 [num_heads][num_seqs*q_len].
+ * Lets attention over disjoint key/value sets be computed separately and merged (pi3b_attn_merge).
+ * replaces: nothing in the reference (its SDPA call is monolithic); exists for the sequence-parallel chunk-global layer
+ *   of BASELINE configs[4], where the local K/V block is attended to while the remote blocks cross NVLink. */
+int pi3b_attn_fwd_hd64_lse(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
+                           int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo, float* lse,
+                           int num_seqs, int q_len, int kv_len, int num_heads, float scale);
+
+/* out[row, 64h + c] = sum_i w_i(row, h) * parts[i][row, 64h + c], w_i = 2^(lses[i] - max_i) / sum_i 2^(lses[i] - max_i):
+ * exact combination of n_parts (1..4) attention results computed over disjoint key/value sets. parts: HOST array of
+ * n_parts device pointers to bf16 [rows, 64*num_heads] (row pitch ld_part); lses: HOST array of device pointers to fp32
+ * [num_heads][rows]; lse_out (optional): merged log-sum-exp. out may alias parts[0].
+ * replaces: nothing in the reference; the softmax of pi3/models/layers/attention.py:336-338 split over key blocks. */
+int pi3b_attn_merge(void* stream, int n_parts, const void* const* parts, const float* const* lses, int64_t ld_part,
+                    void* out, int64_t ldo, float* lse_out, int rows, int num_heads);
 
 /* out[M,D] = LayerNorm(x[M,D]) * gamma + beta (fp32 in; bf16 or fp32 out; in place allowed).
  * If override_rows != NULL, rows r with r % period < n_override are set to override_rows[r % period] instead.
@@ -106,20 +124,23 @@ int pi3b_mask_depth_edge(void* stream, const float* z, int z_stride, const float
 
 /* Sample dense maps at keypoints [N,K,2] (x,y): grid_sample(align_corners=False, border) semantics with
  * g = 2*x/(W-1) - 1; bilinear for points / local_points [N,H,W,3] and images [N,3,H,W] (x255 -> uint8, may be NULL),
- * nearest for conf [N,H,W] and mask [N,H,W] (uint8).
+ * nearest for conf [N,H,W] and mask [N,H,W] (uint8). Bit-exact with what the reference executes (fp32 operation order
+ * of ATen's vectorised CPU grid_sample); grid_math selects how the reference computed g: 1 = keypoints lived on a CUDA
+ * device (ATen multiplies by the fp32 reciprocal of W-1), 0 = on the CPU (true division).
  * replaces: _interpolate_world_points_for_keypoints slam/offline_chunk_creator.py:129-159 and
  *   GridKeypointExtractor._interpolate_colors utils/keypoint_extraction.py:207-229 (CPU grid_sample after a dense D2H). */
 int pi3b_keypoint_gather(void* stream, const float* points, const float* local_points, const float* conf,
                          const uint8_t* mask, const float* images, const float* keypoints, float* out_points,
                          float* out_local, float* out_conf, uint8_t* out_mask, uint8_t* out_colors, int N, int K, int H,
-                         int W);
+                         int W, int grid_math);
 
 /* out_pts[n, i*ws + j, :] = local_points[n, ys[i], xs[j], :]; out_valid = sigmoid(conf) > conf_thr.
  * replaces: the nearest F.interpolate to 64x64 in recover_focal_shift utils/geometry_torch.py:140-142. */
 int pi3b_sample_grid(void* stream, const float* local_points, const float* conf, const int* ys, const int* xs,
                      float* out_pts, uint8_t* out_valid, int N, int H, int W, int hs, int ws, float conf_thr);
 
-/* out2[0] = lower median of a[i*a_stride] / b[i*b_stride] over mask[i] != 0, out2[1] = count.
+/* out2[0] = lower median of a[i*a_stride] / b[i*b_stride] over mask[i] != 0 (NaN if the mask is empty or any masked
+ * ratio is NaN, as torch.median), out2[1] = count.
  * replaces: _get_scale_factor_for_pi3 slam/offline_chunk_creator.py:121-127 (boolean indexing + torch.median). */
 int pi3b_median_ratio(void* stream, const float* a, int a_stride, const float* b, int b_stride, const uint8_t* mask,
                       int n, float* out2);

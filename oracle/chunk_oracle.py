@@ -39,29 +39,32 @@ def scale_factor(moge_depth: torch.Tensor, pi3_depth: torch.Tensor, mask: torch.
     return (moge_depth[mask] / pi3_depth[mask]).median()
 
 
-# ---- grid keypoints: utils/keypoint_extraction.py:53-171 (CPU generator) ----
-def grid_keypoints(num_frames: int, H: int, W: int, max_kp: int) -> torch.Tensor:
+# ---- grid keypoints: utils/keypoint_extraction.py:53-171 (global generator of `device`, as the reference's
+# GridKeypointExtractor(device=...) draws them; 'cuda' is the reference default) ----
+def grid_keypoints(num_frames: int, H: int, W: int, max_kp: int, device="cpu") -> torch.Tensor:
     margin = min(H, W) * 0.05
     eff_h, eff_w = H - 2 * margin, W - 2 * margin
     spacing = int(np.sqrt((eff_h * eff_w) / max_kp))
     spacing = max(8, min(spacing, min(H, W) // 4))
     out = []
     for _ in range(num_frames):
-        gx = torch.arange(margin, W - margin, spacing)
-        gy = torch.arange(margin, H - margin, spacing)
+        gx = torch.arange(margin, W - margin, spacing, device=device)
+        gy = torch.arange(margin, H - margin, spacing, device=device)
         yy, xx = torch.meshgrid(gy, gx, indexing="ij")
         coords = torch.stack([xx.flatten(), yy.flatten()], dim=-1)
         if len(coords) > max_kp:
-            coords = coords[torch.randperm(len(coords))[:max_kp]]
+            coords = coords[torch.randperm(len(coords), device=device)[:max_kp]]
         out.append(coords)
     return torch.stack(out, 0)
 
 
 # ---- sampling at keypoints: offline_chunk_creator.py:129-159, keypoint_extraction.py:207-229 ----
 def _grid(keypoints: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """Normalised grid, evaluated on the keypoints' device and THEN moved to the CPU, as the reference does
+    (`grid = ....cpu()`, offline_chunk_creator.py:143; `grid.cpu()`, keypoint_extraction.py:222)."""
     gx = (keypoints[:, :, 0] / (W - 1)) * 2 - 1
     gy = (keypoints[:, :, 1] / (H - 1)) * 2 - 1
-    return torch.stack([gx, gy], dim=-1).unsqueeze(1)
+    return torch.stack([gx, gy], dim=-1).unsqueeze(1).cpu()
 
 
 def interpolate_at_keypoints(points, local_points, conf, masks, keypoints, H, W) -> Dict[str, torch.Tensor]:

@@ -32,9 +32,9 @@ def _ln(x, sd, prefix, eps):
 
 
 # ---- RoPE-2D: pos_embed.py:112-159 (PyTorch RoPE2D, the path the reference actually takes), freq 100 ----
-def rope_cos_sin(max_pos: int, dtype=torch.float32, base: float = 100.0, d: int = 32):
-    inv_freq = 1.0 / (base ** (torch.arange(0, d, 2).float() / d))
-    t = torch.arange(max_pos + 1, dtype=inv_freq.dtype)
+def rope_cos_sin(max_pos: int, dtype=torch.float32, base: float = 100.0, d: int = 32, device=None):
+    inv_freq = 1.0 / (base ** (torch.arange(0, d, 2, device=device).float() / d))
+    t = torch.arange(max_pos + 1, dtype=inv_freq.dtype, device=device)
     freqs = torch.einsum("i,j->ij", t, inv_freq).to(dtype)
     freqs = torch.cat((freqs, freqs), dim=-1)
     return freqs.cos(), freqs.sin()
@@ -47,7 +47,7 @@ def _rotate_half(x):
 
 def rope2d(tokens: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
     """tokens (B, H, S, 64); positions (B, S, 2) int64 (y, x)."""
-    cos, sin = rope_cos_sin(int(positions.max()), tokens.dtype)
+    cos, sin = rope_cos_sin(int(positions.max()), tokens.dtype, device=tokens.device)
     y, x = tokens.chunk(2, dim=-1)
 
     def apply1d(tok, pos1d):
@@ -56,6 +56,28 @@ def rope2d(tokens: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
         return tok * c + _rotate_half(tok) * s
 
     return torch.cat((apply1d(y, positions[:, :, 0]), apply1d(x, positions[:, :, 1])), dim=-1)
+
+
+def _sdpa(q, k, v):
+    """F.scaled_dot_product_attention(q, k, v) (attention.py:102-104, :336-338), (B, H, S, 64) fp32.
+
+    On the CPU this IS the torch call the reference makes. On a CUDA device (the GPU-side fp32 oracle used by the parity
+    tests at the benchmarked sizes, S up to 100 400) the same softmax(q k^T / sqrt(d)) v is evaluated explicitly in
+    fp32 over blocks of query rows: torch's fused CUDA backends either do not take fp32 (flash) or may use TF32 tensor
+    cores internally (memory-efficient), and the math backend would materialise H*S*S scores at once. Callers switch
+    torch.backends.cuda.matmul.allow_tf32 off, so every product here is a true fp32 GEMM."""
+    if not q.is_cuda:
+        return F.scaled_dot_product_attention(q, k, v)
+    B, H, S, d = q.shape
+    out = torch.empty_like(q)
+    scale = 1.0 / math.sqrt(d)
+    blk = max(64, min(S, (1 << 30) // max(1, B * H * k.shape[2])))     # <= 4 GiB of fp32 scores per block
+    kt = k.transpose(-1, -2)
+    for i in range(0, S, blk):
+        s_blk = torch.matmul(q[:, :, i:i + blk] * scale, kt)
+        out[:, :, i:i + blk] = torch.matmul(torch.softmax(s_blk, dim=-1), v)
+        del s_blk
+    return out
 
 
 # ---- attention: layers/attention.py:94-113 (FlashAttention) and :323-347 (FlashAttentionRope) ----
@@ -69,7 +91,7 @@ def attention(x, sd, prefix, xpos=None, qk_norm=False):
     if xpos is not None:
         q = rope2d(q, xpos)
         k = rope2d(k, xpos)
-    o = F.scaled_dot_product_attention(q, k, v)
+    o = _sdpa(q, k, v)
     o = o.transpose(1, 2).reshape(B, S, C)
     return _linear(o, sd, prefix + ".proj")
 
@@ -127,10 +149,11 @@ def encoder(imgs_norm, sd, taps: Optional[dict] = None):
 
 
 # ---- Pi3.decode: pi3.py:132-171 ; positions: pos_embed.py:162-174 ----
-def positions(bn: int, h: int, w: int) -> torch.Tensor:
-    pos = torch.cartesian_prod(torch.arange(h), torch.arange(w)).view(1, h * w, 2).expand(bn, -1, 2).clone()
+def positions(bn: int, h: int, w: int, device=None) -> torch.Tensor:
+    pos = torch.cartesian_prod(torch.arange(h, device=device), torch.arange(w, device=device))
+    pos = pos.view(1, h * w, 2).expand(bn, -1, 2).clone()
     pos = pos + 1
-    special = torch.zeros(bn, N_SPECIAL, 2, dtype=pos.dtype)
+    special = torch.zeros(bn, N_SPECIAL, 2, dtype=pos.dtype, device=device)
     return torch.cat([special, pos], dim=1)
 
 
@@ -140,7 +163,7 @@ def decode(hidden, sd, N, H, W, taps: Optional[dict] = None):
     reg = sd["register_token"].repeat(B, N, 1, 1).reshape(BN, N_SPECIAL, -1)
     hidden = torch.cat([reg, hidden], dim=1)
     hw = hidden.shape[1]
-    pos = positions(BN, H // PATCH, W // PATCH)
+    pos = positions(BN, H // PATCH, W // PATCH, hidden.device)
     outs = []
     for i in range(36):
         if i % 2 == 0:
@@ -195,7 +218,7 @@ def camera_head(feat, sd, ph, pw):
     feat = F.relu(_linear(feat, sd, "camera_head.more_mlps.2"))
     out_t = _linear(feat, sd, "camera_head.fc_t")
     out_r = _linear(feat, sd, "camera_head.fc_rot")
-    pose = torch.zeros(BN, 4, 4)
+    pose = torch.zeros(BN, 4, 4, device=feat.device)
     pose[:, :3, :3] = svd_orthogonalize(out_r)
     pose[:, :3, 3] = out_t
     pose[:, 3, 3] = 1.0
@@ -205,7 +228,9 @@ def camera_head(feat, sd, ph, pw):
 # ---- Pi3.forward: pi3.py:173-216 ----
 @torch.no_grad()
 def pi3_forward(imgs: torch.Tensor, sd: Dict[str, torch.Tensor], taps: Optional[dict] = None) -> Dict[str, torch.Tensor]:
-    """imgs (B,N,3,H,W) fp32 in [0,1] on CPU; sd: fp32 CPU state_dict with the reference's keys."""
+    """imgs (B,N,3,H,W) fp32 in [0,1]; sd: fp32 state_dict with the reference's keys. CPU tensors: the pinned CPU
+    restatement. CUDA tensors (imgs and sd on the same device): the same functions evaluated on the GPU in fp32 —
+    used by the parity tests at the benchmarked chunk sizes, where the CPU would need hours (see `_sdpa`)."""
     imgs = (imgs - sd["image_mean"]) / sd["image_std"]
     B, N, _, H, W = imgs.shape
     ph, pw = H // PATCH, W // PATCH
@@ -230,6 +255,29 @@ def pi3_forward(imgs: torch.Tensor, sd: Dict[str, torch.Tensor], taps: Optional[
     homog = torch.cat([local_points, torch.ones_like(local_points[..., :1])], dim=-1)
     points = torch.einsum("bnij, bnhwj -> bnhwi", camera_poses, homog)[..., :3]
     return dict(points=points, local_points=local_points, conf=conf, camera_poses=camera_poses)
+
+
+class fp32_strict:
+    """Context manager for the GPU-side oracle: no TF32 anywhere (cuBLAS matmuls and cuDNN convolutions in true fp32)."""
+
+    def __enter__(self):
+        self._mm = torch.backends.cuda.matmul.allow_tf32
+        self._cd = torch.backends.cudnn.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        return self
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self._mm
+        torch.backends.cudnn.allow_tf32 = self._cd
+        return False
+
+
+def pi3_forward_gpu_fp32(imgs: torch.Tensor, sd: Dict[str, torch.Tensor], device="cuda") -> Dict[str, torch.Tensor]:
+    """The oracle forward evaluated on a CUDA device in strict fp32 (see `_sdpa`); returns CUDA tensors."""
+    sd_dev = {k: v.to(device=device, dtype=torch.float32) for k, v in sd.items()}
+    with fp32_strict():
+        return pi3_forward(imgs.to(device=device, dtype=torch.float32), sd_dev)
 
 
 # ---- error metrics used by the parity tests ----

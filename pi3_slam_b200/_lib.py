@@ -26,6 +26,11 @@ SIGNATURES = {
     # stream, q, k, v, ldq, ldk, ldv, q_col0, k_col0, v_col0, out, ldo, num_seqs, q_len, kv_len, num_heads, scale
     "pi3b_attn_fwd_hd64": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64,
                                    c_int, c_int, c_int, c_int, c_float]),
+    # stream, q, k, v, ldq, ldk, ldv, q_col0, k_col0, v_col0, out, ldo, lse, num_seqs, q_len, kv_len, num_heads, scale
+    "pi3b_attn_fwd_hd64_lse": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64, _P,
+                                       c_int, c_int, c_int, c_int, c_float]),
+    # stream, n_parts, parts(host void*[n]), lses(host float*[n]), ld_part, out, ldo, lse_out, rows, num_heads
+    "pi3b_attn_merge": (c_int, [_P, c_int, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int]),
     # stream, x, ldx, gamma, beta, eps, out, ldo, out_f32, M, D, override_rows, period, n_override
     "pi3b_layernorm": (c_int, [_P, _P, c_int64, _P, _P, c_float, _P, c_int64, c_int, c_int, c_int, _P, c_int, c_int]),
     # stream, qkv, ld, M, heads, tokens_per_frame, n_special, patch_w, qn_w, qn_b, kn_w, kn_b, eps, cs_table, table_rows, do_rope
@@ -46,8 +51,8 @@ SIGNATURES = {
     "pi3b_pose_from_9d": (c_int, [_P, _P, c_int64, _P, c_int64, _P, c_int]),
     # stream, z, z_stride, conf, mask, N, H, W, conf_thr, rtol
     "pi3b_mask_depth_edge": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_float, c_float]),
-    # stream, points, local_points, conf, mask, images, keypoints, out_points, out_local, out_conf, out_mask, out_colors, N, K, H, W
-    "pi3b_keypoint_gather": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int]),
+    # stream, points, local_points, conf, mask, images, keypoints, out_points, out_local, out_conf, out_mask, out_colors, N, K, H, W, grid_math
+    "pi3b_keypoint_gather": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int]),
     # stream, local_points, conf, ys, xs, out_pts, out_valid, N, H, W, hs, ws, conf_thr
     "pi3b_sample_grid": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float]),
     # stream, a, a_stride, b, b_stride, mask, n, out2

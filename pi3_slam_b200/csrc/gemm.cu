@@ -359,11 +359,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                        cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N, STAGES>;
   auto kern = gemm_kernel<BLOCK_N, STAGES, TF32, CL>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;   // one per template instantiation; the attribute is per device
+  const int dev = current_device();
+  if (configured.first_call_on(dev)) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
       return check_launch("gemm: cudaFuncSetAttribute");
-    configured = true;
+    configured.done(dev);
   }
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
   const int units = ((num_m + CL - 1) / CL) * ((p.N + BLOCK_N - 1) / BLOCK_N);
@@ -389,17 +390,6 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return check_launch("gemm launch");
 }
 
-static int cached_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 }  // namespace pi3b
 
 using namespace pi3b;
@@ -421,7 +411,7 @@ extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda,
   const int vec_ok = (ldo % (out_f32 ? 4 : 8) == 0) && al16(out) && (!resid || (ld_resid % 4 == 0 && al16(resid))) &&
                      (!bias || al16(bias)) && (!gamma || al16(gamma));
 
-  const int num_sms = cached_num_sms();
+  const int num_sms = num_sms_of(current_device());
   const int block_k = 128 / esz;
   // Use the wide tile when it still fills the machine; otherwise the narrow tile for more CTAs.
   const int tiles256 = ((M + 127) / 128) * ((N + 255) / 256);

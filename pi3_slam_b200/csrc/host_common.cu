@@ -26,6 +26,22 @@ int check_launch(const char* what) {
   return PI3B_OK;
 }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
+int num_sms_of(int dev) {
+  static std::atomic<int> cache[kMaxDevices] = {};
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace pi3b {
 
 enum : int {
@@ -24,6 +26,18 @@ int check_launch(const char* what);
 // dtype: 0 = bf16, 1 = fp32.
 int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                  uint32_t box_rows, uint32_t box_cols);
+
+// Per-device state. Function attributes (opt-in shared memory) and the SM count belong to a device, not to the process:
+// a process that drives several GPUs, or several host threads racing through their first call, must each see them set.
+constexpr int kMaxDevices = 64;
+int current_device();          // cudaGetDevice, clamped to [0, kMaxDevices)
+int num_sms_of(int dev);       // cached cudaDevAttrMultiProcessorCount
+struct DeviceOnce {
+  std::atomic<unsigned char> flag[kMaxDevices] = {};
+  // true until done(dev) has been called: concurrent first callers may both run the (idempotent) setup
+  bool first_call_on(int dev) const { return flag[dev].load(std::memory_order_acquire) == 0; }
+  void done(int dev) { flag[dev].store(1, std::memory_order_release); }
+};
 
 }  // namespace pi3b
 

@@ -9,14 +9,22 @@ namespace pi3b {
 
 // ------------------------------------------------------------------------------------------------
 // Keypoint gather. Reference: offline_chunk_creator.py:129-159 and keypoint_extraction.py:207-229:
-//   g = (x / (W-1)) * 2 - 1;  F.grid_sample(align_corners=False, padding_mode='border')
-//   => source coordinate ix = ((g + 1) * W - 1) / 2 clipped to [0, W-1]; bilinear for points,
-//   local_points and colours (x255, truncated to uint8), nearest (round-half-even) for conf and mask.
-// One thread per (frame, keypoint); the arithmetic follows ATen's fp32 op order.
+//   g = (x / (W-1)) * 2 - 1  (torch elementwise ops on the keypoints' device), then, on the CPU,
+//   F.grid_sample(align_corners=False, padding_mode='border'); bilinear for points, local_points and colours
+//   (x255, truncated to uint8), nearest (round-half-even) for conf and mask.
+// The outputs are byte / index work downstream, so the kernel restates the exact fp32 operation order of what the
+// reference executes (identified empirically against torch 2.11 CPU, scripts/probe_grid_sample_order.py):
+//   * grid: on a CUDA tensor ATen divides by a scalar as a multiplication by its fp32 reciprocal (grid_math = 1);
+//     on a CPU tensor it is a true division (grid_math = 0);
+//   * ATen's vectorised CPU grid_sample (AVX2 / AVX-512 builds, FMA-contracted): ix = fma(g + 1, W / 2, -0.5) clipped to
+//     [0, W-1]; w = ix - floor(ix), e = 1 - w (likewise n, s); out = fma(se_v, n*w, fma(sw_v, n*e, fma(ne_v, s*w,
+//     nw_v * (s*e)))) with out-of-range corners read as 0.
+// One thread per (frame, keypoint).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float src_index(float coord, int size) {
-  const float g = __fsub_rn(__fmul_rn(__fdiv_rn(coord, float(size - 1)), 2.0f), 1.0f);
-  float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), float(size)), 1.0f), 2.0f);
+__device__ __forceinline__ float src_index(float coord, int size, int grid_math) {
+  const float q = grid_math ? __fmul_rn(coord, __fdiv_rn(1.0f, float(size - 1))) : __fdiv_rn(coord, float(size - 1));
+  const float g = __fsub_rn(__fmul_rn(q, 2.0f), 1.0f);
+  float ix = __fmaf_rn(__fadd_rn(g, 1.0f), __fdiv_rn(float(size), 2.0f), -0.5f);
   ix = fminf(float(size - 1), fmaxf(ix, 0.0f));
   return ix;
 }
@@ -25,29 +33,27 @@ __global__ void __launch_bounds__(128) keypoint_gather_kernel(
     const float* __restrict__ points, const float* __restrict__ local_points, const float* __restrict__ conf,
     const uint8_t* __restrict__ mask, const float* __restrict__ images, const float* __restrict__ kps,
     float* __restrict__ o_points, float* __restrict__ o_local, float* __restrict__ o_conf, uint8_t* __restrict__ o_mask,
-    uint8_t* __restrict__ o_colors, int N, int K, int H, int W) {
+    uint8_t* __restrict__ o_colors, int N, int K, int H, int W, int grid_math) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= N * K) return;
   const int n = gid / K;
-  const float ix = src_index(kps[gid * 2 + 0], W);
-  const float iy = src_index(kps[gid * 2 + 1], H);
+  const float ix = src_index(kps[gid * 2 + 0], W, grid_math);
+  const float iy = src_index(kps[gid * 2 + 1], H, grid_math);
   const float x0f = floorf(ix), y0f = floorf(iy);
   const int x0 = int(x0f), y0 = int(y0f), x1 = x0 + 1, y1 = y0 + 1;
-  const float w_nw = __fmul_rn(__fsub_rn(x0f + 1.0f, ix), __fsub_rn(y0f + 1.0f, iy));
-  const float w_ne = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(y0f + 1.0f, iy));
-  const float w_sw = __fmul_rn(__fsub_rn(x0f + 1.0f, ix), __fsub_rn(iy, y0f));
-  const float w_se = __fmul_rn(__fsub_rn(ix, x0f), __fsub_rn(iy, y0f));
+  const float w = __fsub_rn(ix, x0f), e = __fsub_rn(1.0f, w);
+  const float nn = __fsub_rn(iy, y0f), s = __fsub_rn(1.0f, nn);
+  const float w_nw = __fmul_rn(s, e), w_ne = __fmul_rn(s, w), w_sw = __fmul_rn(nn, e), w_se = __fmul_rn(nn, w);
   const bool in_x0 = x0 >= 0 && x0 < W, in_x1 = x1 >= 0 && x1 < W;
   const bool in_y0 = y0 >= 0 && y0 < H, in_y1 = y1 >= 0 && y1 < H;
   const size_t fbase = size_t(n) * H * W;
 
   auto bil = [&](const float* src, size_t stride) {
-    float acc = 0.f;
-    if (in_y0 && in_x0) acc = __fadd_rn(acc, __fmul_rn(src[(size_t(y0) * W + x0) * stride], w_nw));
-    if (in_y0 && in_x1) acc = __fadd_rn(acc, __fmul_rn(src[(size_t(y0) * W + x1) * stride], w_ne));
-    if (in_y1 && in_x0) acc = __fadd_rn(acc, __fmul_rn(src[(size_t(y1) * W + x0) * stride], w_sw));
-    if (in_y1 && in_x1) acc = __fadd_rn(acc, __fmul_rn(src[(size_t(y1) * W + x1) * stride], w_se));
-    return acc;
+    const float v_nw = (in_y0 && in_x0) ? src[(size_t(y0) * W + x0) * stride] : 0.f;
+    const float v_ne = (in_y0 && in_x1) ? src[(size_t(y0) * W + x1) * stride] : 0.f;
+    const float v_sw = (in_y1 && in_x0) ? src[(size_t(y1) * W + x0) * stride] : 0.f;
+    const float v_se = (in_y1 && in_x1) ? src[(size_t(y1) * W + x1) * stride] : 0.f;
+    return __fmaf_rn(v_se, w_se, __fmaf_rn(v_sw, w_sw, __fmaf_rn(v_ne, w_ne, __fmul_rn(v_nw, w_nw))));
   };
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -116,9 +122,21 @@ __global__ void __launch_bounds__(1024) median_ratio_kernel(const float* __restr
     if (tid == 0) { out[0] = __int_as_float(0x7fc00000); out[1] = 0.f; }
     return;
   }
-  // NaN ratios sort last in torch.median's ordering; map them to the largest key
-  if (tid == 0) { s_prefix = 0; s_rank = (count - 1) / 2; }
+  // torch.median propagates NaN: if ANY masked ratio is NaN (0/0, inf/inf) the result is NaN, whatever its rank
+  __shared__ unsigned int s_nan;
+  if (tid == 0) { s_prefix = 0; s_rank = (count - 1) / 2; s_nan = 0; }
   __syncthreads();
+  {
+    unsigned int any_nan = 0;
+    for (int i = tid; i < n; i += blockDim.x)
+      if (mask[i]) any_nan |= isnan(a[size_t(i) * a_stride] / b[size_t(i) * b_stride]) ? 1u : 0u;
+    if (any_nan) atomicOr(&s_nan, 1u);
+  }
+  __syncthreads();
+  if (s_nan) {
+    if (tid == 0) { out[0] = __int_as_float(0x7fc00000); out[1] = float(count); }
+    return;
+  }
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
@@ -289,15 +307,16 @@ using namespace pi3b;
 extern "C" int pi3b_keypoint_gather(void* stream, const float* points, const float* local_points, const float* conf,
                                     const uint8_t* mask, const float* images, const float* keypoints, float* out_points,
                                     float* out_local, float* out_conf, uint8_t* out_mask, uint8_t* out_colors, int N,
-                                    int K, int H, int W) {
+                                    int K, int H, int W, int grid_math) {
   PI3B_REQUIRE(points && local_points && conf && mask && keypoints && out_points && out_local && out_conf && out_mask,
                "pi3b_keypoint_gather: null pointer");
   PI3B_REQUIRE(!images || out_colors, "pi3b_keypoint_gather: images given without out_colors");
   PI3B_REQUIRE(N > 0 && K > 0 && H > 1 && W > 1, "pi3b_keypoint_gather: bad shape");
+  PI3B_REQUIRE(grid_math == 0 || grid_math == 1, "pi3b_keypoint_gather: grid_math must be 0 (CPU) or 1 (CUDA)");
   const int total = N * K;
   keypoint_gather_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       points, local_points, conf, mask, images, keypoints, out_points, out_local, out_conf, out_mask, out_colors, N, K,
-      H, W);
+      H, W, grid_math);
   return check_launch("keypoint_gather launch");
 }
 

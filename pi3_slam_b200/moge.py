@@ -379,6 +379,7 @@ class MoGeModel(nn.Module):
         if not image.is_cuda:
             raise _lib.Pi3bError("pi3_slam_b200.MoGeModel runs on CUDA (sm_100a) only; there is no CPU fallback")
 
+    @ops.device_guard(lambda self, image, *a: image)
     @torch.no_grad()
     def forward(self, image: torch.Tensor, num_tokens: int) -> Dict[str, torch.Tensor]:
         """image (B,3,H,W) in [0,1] -> points (B,H,W,3), mask (B,H,W) probability, metric_scale (B,) [, normal]."""
@@ -396,6 +397,7 @@ class MoGeModel(nn.Module):
                     res.setdefault(key, []).append(o[key])
         return {k: (torch.cat(v) if k == "metric_scale" else torch.stack(v)) for k, v in res.items()}
 
+    @ops.device_guard(lambda self, image, *a: image)
     @torch.inference_mode()
     def infer(self, image: torch.Tensor, num_tokens: int = None, resolution_level: int = 9, force_projection: bool = True,
               apply_mask: bool = True, fov_x=None, use_fp16: bool = True) -> Dict[str, torch.Tensor]:

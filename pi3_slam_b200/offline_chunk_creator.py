@@ -161,11 +161,15 @@ class OfflineChunkCreator:
         return ops.median_ratio(a, b, m)[0]
 
     @staticmethod
-    def _interpolate_world_points_for_keypoints(dense: Dict, keypoints: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """Sample points / local_points (bilinear) and conf / masks (nearest) at keypoints (reference :129-159)."""
+    def _interpolate_world_points_for_keypoints(dense: Dict, keypoints: torch.Tensor,
+                                                grid_on_cuda: bool = True) -> Dict[str, torch.Tensor]:
+        """Sample points / local_points (bilinear) and conf / masks (nearest) at keypoints (reference :129-159).
+        `grid_on_cuda`: where the reference would have evaluated `(kp / (W-1)) * 2 - 1` — on the device its keypoints
+        live on (torch-CUDA and torch-CPU round the division differently; the kernel reproduces either bit for bit)."""
         images = dense.get("images")
         p, l, c, m, col = ops.keypoint_gather(dense["points"], dense["local_points"], dense["conf"],
-                                              dense["masks"].to(torch.uint8).contiguous(), images, keypoints)
+                                              dense["masks"].to(torch.uint8).contiguous(), images, keypoints,
+                                              grid_on_cuda=grid_on_cuda)
         return {"points": p, "local_points": l, "conf": c, "masks": m, "colors": col}
 
     def _frames_to_device(self, frames_host: torch.Tensor) -> torch.Tensor:
@@ -189,6 +193,7 @@ class OfflineChunkCreator:
         return out[None]
 
     # ------------------------------------------------------------------ one chunk
+    @ops.device_guard(lambda self, *a: self.config.device)
     def _process_single_chunk(self, chunk_images: torch.Tensor, chunk_paths: List[str]) -> Dict:
         assert chunk_images.ndim == 5, "Expected (B=1, N, C, H, W) tensor for chunk images"
         dev = self.config.device
@@ -209,6 +214,7 @@ class OfflineChunkCreator:
             self.last_device_seconds = float(ev0.elapsed_time(ev1) * 1e-3)
             return self._finish_chunk(pi3_result, imgs_dev, chunk_paths, _metrics)
 
+    @ops.device_guard(lambda self, *a: self.config.device)
     def _process_chunk_sequence_parallel(self, frames_host: torch.Tensor, num_frames: int,
                                          chunk_paths: List, ranks: Tuple[int, ...], group) -> Optional[Dict]:
         """One chunk on a group of ranks (the tail waves of `plan_waves`): every rank runs the forward on its
@@ -252,6 +258,7 @@ class OfflineChunkCreator:
         """Everything of `_process_single_chunk` after the forward (reference :175-256)."""
         return self._enqueue_finish(pi3_result, imgs_dev, chunk_paths, _metrics).finish()
 
+    @ops.device_guard(lambda self, *a: self.config.device)
     def _enqueue_finish(self, pi3_result: Dict[str, torch.Tensor], imgs_dev: torch.Tensor, chunk_paths: List,
                         _metrics: Dict, fwd_events=None) -> "_PendingChunk":
         """Device half of the post-processing: masks, metric scale, the 64x64 samples for the intrinsics solve, the
@@ -299,7 +306,7 @@ class OfflineChunkCreator:
                     H, W = imgs_dev.shape[-2:]
                     kp_res = self.keypoint_extractor.extract(num_frames, H, W)
                     kps = kp_res["keypoints"].to(dev, torch.float32).contiguous()
-                    interp = self._interpolate_world_points_for_keypoints(dense, kps)
+                    interp = self._interpolate_world_points_for_keypoints(dense, kps, kp_res["keypoints"].is_cuda)
                     pend.staged["points"] = stage(interp["points"].to(torch.float16))
                     pend.staged["local_points"] = stage(interp["local_points"].to(torch.float16))
                     pend.staged["conf"] = stage(interp["conf"].to(torch.float16))
@@ -338,6 +345,7 @@ class OfflineChunkCreator:
         return sorted((e for part in gathered for e in part), key=lambda e: e["chunk_index"])
 
     # ------------------------------------------------------------------ whole sequence
+    @ops.device_guard(lambda self, *a: self.config.device)
     def process_and_save(self, image_paths: Sequence, loader: Optional[Callable] = None,
                          target_size: Optional[Tuple[int, int]] = None, distributed: Optional[bool] = None) -> List[str]:
         """Process the sequence in chunks and save one file per chunk; returns the files this rank wrote.

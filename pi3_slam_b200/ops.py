@@ -14,8 +14,38 @@ from . import _lib
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
 
+def device_guard(get_device):
+    """Method decorator: run the method with `get_device(self, *args)` (a CUDA torch.device / str / tensor) as the
+    current CUDA device. Every C-ABI launch inside then goes to that device's stream, function attributes and SM count."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(self, *args, **kwargs):
+            d = get_device(self, *args)
+            if torch.is_tensor(d):
+                d = d.device
+            d = torch.device(d) if d is not None else None
+            if d is None or d.type != "cuda":
+                return fn(self, *args, **kwargs)      # the method itself rejects non-CUDA inputs loudly
+            with torch.cuda.device(d):
+                return fn(self, *args, **kwargs)
+        return wrapper
+    return deco
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device_of(t: torch.Tensor):
+    """Context manager that makes `t`'s device current. The C ABI launches on the CURRENT device (the stream handle,
+    the opt-in shared-memory attributes and the SM count are all per device), so callers that may be handed tensors of
+    another GPU (`OfflineCreatorConfig.device='cuda:1'`, `Pi3.forward` on a non-default device) wrap their launch
+    sequence in this once instead of paying a device switch per kernel."""
+    if not t.is_cuda:
+        raise _lib.Pi3bError("expected a CUDA tensor (no CPU fallback)")
+    return torch.cuda.device(t.device)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -96,6 +126,45 @@ def attention_q_kv(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, num_seq
                                 kv.stride(0), q_col0, 0, C, out.data_ptr(), out.stride(0), num_seqs, q_len, kv_len,
                                 num_heads, scale)
     _lib.check(rc, "pi3b_attn_fwd_hd64")
+    return out
+
+
+def attention_q_kv_lse(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, num_seqs: int,
+                       q_len: int, kv_len: int, num_heads: int = 16, scale: float = 0.125, q_col0: int = 0) -> None:
+    """`attention_q_kv` that also writes the log2-domain log-sum-exp of every (head, query row) into `lse`
+    (fp32 [num_heads, num_seqs*q_len]) so that results over disjoint key/value sets can be merged."""
+    lib = _lib.load()
+    _req(q, torch.bfloat16, "q"); _req(kv, torch.bfloat16, "kv"); _req(out, torch.bfloat16, "out")
+    _req(lse, torch.float32, "lse")
+    C = num_heads * 64
+    assert q.stride(1) == 1 and kv.stride(1) == 1 and out.stride(1) == 1 and lse.is_contiguous()
+    assert q.shape[0] == num_seqs * q_len and kv.shape[0] == num_seqs * kv_len and kv.shape[1] == 2 * C
+    assert out.shape == (q.shape[0], C) and lse.shape == (num_heads, q.shape[0])
+    rc = lib.pi3b_attn_fwd_hd64_lse(_stream(), q.data_ptr(), kv.data_ptr(), kv.data_ptr(), q.stride(0), kv.stride(0),
+                                    kv.stride(0), q_col0, 0, C, out.data_ptr(), out.stride(0), lse.data_ptr(), num_seqs,
+                                    q_len, kv_len, num_heads, scale)
+    _lib.check(rc, "pi3b_attn_fwd_hd64_lse")
+
+
+def attention_merge(parts, lses, out: torch.Tensor, num_heads: int = 16, lse_out: Optional[torch.Tensor] = None):
+    """out = exact softmax-weighted combination of 1..4 partial attention results (bf16 [rows, 64*heads], equal row
+    pitch) with their log-sum-exps (fp32 [heads, rows]). `out` may alias parts[0]."""
+    import ctypes
+    lib = _lib.load()
+    n = len(parts)
+    assert 1 <= n <= 4 and len(lses) == n
+    rows = out.shape[0]
+    ld = parts[0].stride(0)
+    for t, l in zip(parts, lses):
+        _req(t, torch.bfloat16, "part"); _req(l, torch.float32, "lse")
+        assert t.shape == out.shape and t.stride(1) == 1 and t.stride(0) == ld
+        assert l.is_contiguous() and l.shape == (num_heads, rows)
+    _req(out, torch.bfloat16, "out")
+    pa = (ctypes.c_void_p * n)(*[t.data_ptr() for t in parts])
+    la = (ctypes.c_void_p * n)(*[l.data_ptr() for l in lses])
+    rc = lib.pi3b_attn_merge(_stream(), n, ctypes.cast(pa, ctypes.c_void_p), ctypes.cast(la, ctypes.c_void_p), ld,
+                             out.data_ptr(), out.stride(0), _ptr(lse_out), rows, num_heads)
+    _lib.check(rc, "pi3b_attn_merge")
     return out
 
 
@@ -222,10 +291,11 @@ def mask_depth_edge(local_points: torch.Tensor, conf: torch.Tensor, mask: torch.
     return mask
 
 
-def keypoint_gather(points, local_points, conf, mask, images, keypoints):
+def keypoint_gather(points, local_points, conf, mask, images, keypoints, grid_on_cuda: bool = True):
     """Sample dense maps at keypoints (N,K,2) (x, y): bilinear points / local_points / colours (uint8),
     nearest conf / mask. Returns (points (N,K,3) f32, local (N,K,3) f32, conf (N,K,1) f32, mask (N,K,1) bool,
-    colors (N,K,3) uint8 or None)."""
+    colors (N,K,3) uint8 or None). Bit-exact with the reference's torch ops; `grid_on_cuda` says on which device the
+    reference would have computed the normalised grid (where its keypoints live): CUDA (default extractor) or CPU."""
     lib = _lib.load()
     for t, nm in ((points, "points"), (local_points, "local_points"), (conf, "conf"), (keypoints, "keypoints")):
         _req(t, torch.float32, nm)
@@ -243,7 +313,7 @@ def keypoint_gather(points, local_points, conf, mask, images, keypoints):
         o_col = torch.empty(N, K, 3, device=dev, dtype=torch.uint8)
     rc = lib.pi3b_keypoint_gather(_stream(), points.data_ptr(), local_points.data_ptr(), conf.data_ptr(),
                                   mask.data_ptr(), _ptr(images), keypoints.data_ptr(), o_p.data_ptr(), o_l.data_ptr(),
-                                  o_c.data_ptr(), o_m.data_ptr(), _ptr(o_col), N, K, H, W)
+                                  o_c.data_ptr(), o_m.data_ptr(), _ptr(o_col), N, K, H, W, 1 if grid_on_cuda else 0)
     _lib.check(rc, "pi3b_keypoint_gather")
     return o_p, o_l, o_c, o_m.bool(), o_col
 

@@ -102,9 +102,11 @@ class Pi3(nn.Module):
             sd = torch.load(weights, map_location="cpu")
             if isinstance(sd, dict) and "state_dict" in sd:
                 sd = sd["state_dict"]
-        # buffers are not always serialised by older checkpoints
-        missing = [k for k in ("image_mean", "image_std") if k not in sd]
-        model.load_state_dict(sd, strict=not missing)
+        # the two normalisation buffers are not always serialised by older checkpoints; nothing else may be absent
+        res = model.load_state_dict(sd, strict=False)
+        missing = [k for k in res.missing_keys if k not in ("image_mean", "image_std")]
+        if missing or res.unexpected_keys:
+            raise RuntimeError(f"checkpoint does not match Pi3: missing {missing[:8]} unexpected {res.unexpected_keys[:8]}")
         return model
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
@@ -292,6 +294,12 @@ class Pi3(nn.Module):
         B, N, _, H, W = imgs.shape
         if H % PATCH or W % PATCH:
             raise ValueError("H and W must be multiples of 14")
+        # the C ABI launches on the CURRENT device and stream: make the frames' device current for the whole schedule
+        with ops.on_device_of(imgs):
+            return self._forward_on_device(imgs, taps, sp_group, sp_world)
+
+    def _forward_on_device(self, imgs, taps, sp_group, sp_world) -> Dict[str, torch.Tensor]:
+        B, N, _, H, W = imgs.shape
         device = imgs.device
         pk = self._pack(device)
         sc = self._shape_consts(H, W, device)

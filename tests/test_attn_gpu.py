@@ -13,8 +13,8 @@ def _ref(qkv, B, S, H):
 
 # (num_seqs, seq_len, heads): frame-local shapes (T=261, 643, 1004), multiples of the tile sizes, ragged
 # tails on both the Q and the KV side, and a chunk-global shape.
-# Sequences up to 8192 keys run the four-tile kernel (revision 9), longer ones the three-tile kernel (revision 8): both
-# sides of the dispatch are covered, and test_every_revision_when_forced pins each kernel on both kinds of shape.
+# Sequences up to 8192 keys run the four-tile kernel, longer ones the three-tile kernel: both sides of the dispatch are
+# covered, and test_each_kernel_when_forced pins each kernel on both kinds of shape.
 CASES = [(1, 128, 1), (1, 256, 2), (2, 384, 2), (3, 261, 16), (2, 643, 4), (2, 1004, 16), (1, 5, 1), (1, 129, 2),
          (1, 8 * 261, 16), (1, 4099, 3), (1, 9001, 2), (1, 8193, 1)]
 
@@ -71,10 +71,10 @@ def test_attention_local_queries_against_longer_kv():
         assert err.item() < 1e-2, f"rows {lo}:{hi} rel err {err.item():.3e}"
 
 
-@pytest.mark.parametrize("rev", [5, 8, 9])
-def test_every_revision_when_forced(rev):
-    """PI3B_ATTN_REV pins one kernel for every shape (the library reads it once per process, hence the subprocess):
-    each revision must be correct on short ragged sequences and on a long one, whatever the default dispatch picks."""
+@pytest.mark.parametrize("rev", [3, 4])
+def test_each_kernel_when_forced(rev):
+    """PI3B_ATTN_TILES pins one kernel for every shape (the library reads it once per process, hence the subprocess):
+    each kernel must be correct on short ragged sequences and on a long one, whatever the default dispatch picks."""
     import os
     import subprocess
     import sys
@@ -95,8 +95,40 @@ for (B, S, H) in [(2, 643, 4), (1, 129, 2), (1, 8700, 1)]:
     worst = max(worst, float((out.float() - ref).norm() / ref.norm()))
 print("WORST", worst)
 """ % root
-    env = dict(os.environ, PI3B_ATTN_REV=str(rev))
+    env = dict(os.environ, PI3B_ATTN_TILES=str(rev))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0, r.stderr[-2000:]
     worst = float(r.stdout.strip().split("WORST")[-1])
-    assert worst < 1e-2, f"revision {rev}: rel err {worst:.3e}"
+    assert worst < 1e-2, f"{rev}-tile kernel: rel err {worst:.3e}"
+
+
+@pytest.mark.parametrize("S,H,splits", [(1100, 4, (0, 300, 829, 1100)), (9000, 2, (0, 4000, 9000)),
+                                        (700, 16, (0, 64, 65, 700))])
+def test_lse_and_merge_over_key_blocks(S, H, splits):
+    """Attention over disjoint key/value blocks + pi3b_attn_merge == attention over all keys (the sequence-parallel
+    chunk-global layer overlaps the remote blocks' NVLink transfer with the local block's attention this way)."""
+    from pi3_slam_b200 import ops
+
+    torch.manual_seed(S)
+    qkv = (torch.randn(S, 3 * H * 64, device="cuda") * 1.3).bfloat16()
+    ref = _ref(qkv, 1, S, H)
+    parts, lses = [], []
+    for lo, hi in zip(splits[:-1], splits[1:]):
+        kv = qkv[lo:hi, H * 64:].contiguous()
+        o = torch.empty(S, H * 64, device="cuda", dtype=torch.bfloat16)
+        l = torch.empty(H, S, device="cuda", dtype=torch.float32)
+        ops.attention_q_kv_lse(qkv, kv, o, l, 1, S, hi - lo, H)
+        parts.append(o); lses.append(l)
+    out = torch.empty(S, H * 64, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(H, S, device="cuda", dtype=torch.float32)
+    ops.attention_merge(parts, lses, out, H, lse_out=lse)
+    err = (out.float() - ref).norm() / ref.norm()
+    assert err.item() < 1e-2, f"merged rel err {err.item():.3e}"
+    # merged log-sum-exp equals the fp64 one (log2 domain, scale 1/8)
+    q, k, _ = qkv.double().view(S, 3, H, 64).permute(1, 2, 0, 3)
+    want = torch.logsumexp(q @ k.transpose(-1, -2) * 0.125, dim=-1) / 0.6931471805599453
+    assert (lse.double() - want).abs().max().item() < 2e-2
+    # a single part passes through unchanged
+    one = torch.empty_like(out)
+    ops.attention_merge(parts[:1], lses[:1], one, H)
+    assert torch.equal(one, parts[0])
