@@ -51,15 +51,7 @@ namespace pi3b {
 #ifndef PI3B_POLY_DEG
 #define PI3B_POLY_DEG 2
 #endif
-// PI3B_POLY_LEGACY: round-1 mix (1 of 8 elements, scalar degree-3 polynomial) kept selectable for the A/B baseline
-#ifndef PI3B_POLY_LEGACY
-#define PI3B_POLY_LEGACY 0
-#endif
-// PI3B_FENCE_LEAN: drop tcgen05.fence::before_thread_sync after tcgen05.wait::ld / wait::st (the wait already orders the
-// TMEM access before the mbarrier arrive)
-#ifndef PI3B_FENCE_LEAN
-#define PI3B_FENCE_LEAN 0
-#endif
+
 
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
 constexpr int kKvBytes = 64 * 128;     // 64 rows x 64 bf16
@@ -109,16 +101,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-// scalar exp2 on the FMA/ALU pipes (round-1 mix): Cody-Waite split + degree-3 minimax polynomial, rel. error 1e-4
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;            // 1.5 * 2^23: rounds x to the nearest integer n in the low mantissa bits
-  const float f = x - (t - 12582912.0f);       // f in [-0.5, 0.5]
-  float p = fmaf(0.0555041086f, f, 0.2402265069f);
-  p = fmaf(p, f, 0.6931471806f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // p * 2^n
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
@@ -180,12 +162,6 @@ __device__ __forceinline__ void exp_block(uint32_t* a, uint64_t sc2, uint64_t ne
   for (int c = 0; c < NCOL; c += 2) {
     const uint64_t x = ffma2(pack2(__uint_as_float(a[c]), __uint_as_float(a[c + 1])), sc2, negm2);
     float p0, p1;
-#if PI3B_POLY_LEGACY
-    float x0, x1;
-    unpack2(x, x0, x1);
-    p0 = (c % 8 == 0) ? poly_exp2(x0) : fast_exp2(x0);
-    p1 = fast_exp2(x1);
-#else
     // pairs are spread evenly over the row so that ptxas can interleave the FMA-pipe chains with the MUFU stream
     const bool poly = (((c >> 1) % 8) * PI3B_POLY_PAIRS) % 8 < PI3B_POLY_PAIRS;
     if (poly) {
@@ -196,7 +172,6 @@ __device__ __forceinline__ void exp_block(uint32_t* a, uint64_t sc2, uint64_t ne
       p0 = fast_exp2(x0);
       p1 = fast_exp2(x1);
     }
-#endif
     lsum = fadd2(lsum, pack2(p0, p1));
     a[c >> 1] = pack_bf16x2(p0, p1);
   }
@@ -301,11 +276,8 @@ __device__ __forceinline__ void tma_producer(uint8_t* smem_q, uint8_t* smem_k, u
   }
 }
 
-__device__ __forceinline__ void softmax_release_fence() {
-#if !PI3B_FENCE_LEAN
-  tc_fence_before();
-#endif
-}
+// (dropping this fence after tcgen05.wait::ld / wait::st measured no gain: profiles/r02_attn_poly_ab.log, "lean")
+__device__ __forceinline__ void softmax_release_fence() { tc_fence_before(); }
 
 // =====================================================================================================================
 // Three-tile kernel (kv_len > 8192)

@@ -29,6 +29,18 @@ def shard_chunks(num_chunks: int, rank: int, world_size: int) -> List[int]:
     return list(range(rank, num_chunks, world_size))
 
 
+def split_frames(num_frames: int, group_size: int) -> List[Tuple[int, int]]:
+    """(first_frame, count) of every rank of a sequence-parallel group: contiguous, as even as possible, the first
+    num_frames % group_size ranks hold one frame more."""
+    base, extra = divmod(num_frames, group_size)
+    out, start = [], 0
+    for i in range(group_size):
+        n = base + (1 if i < extra else 0)
+        out.append((start, n))
+        start += n
+    return out
+
+
 def plan_waves(frames_per_chunk: Sequence[int], world_size: int, allow_sp: bool = True) -> List[List[Tuple[int, Tuple[int, ...]]]]:
     """Hybrid schedule for a sequence of independent chunks on `world_size` GPUs.
 
@@ -37,9 +49,10 @@ def plan_waves(frames_per_chunk: Sequence[int], world_size: int, allow_sp: bool 
     largest divisor of world_size not above the number of remaining chunks) and each group runs ONE chunk
     sequence-parallel (frames split over the group, K/V all-gathered in the chunk-global layers), so the last wave
     does not leave GPUs idle: 13 chunks on 8 GPUs = 8 singles, then 4 chunks on 4 pairs, then the 40-frame tail on all
-    8 (makespan 1.53 chunk-times instead of 2). A chunk whose frame count is not divisible by the group size falls back
-    to the largest group size that divides it. With allow_sp=False this is plain round-robin sharding (chunk i on rank
-    i % world_size), identical to `shard_chunks`."""
+    8 (makespan 1.53 chunk-times instead of 2). Frames are split as evenly as possible (`split_frames`: the first
+    n % g ranks of a group hold one frame more); a group is only shrunk when the chunk has fewer frames than ranks.
+    With allow_sp=False this is plain round-robin sharding (chunk i on rank i % world_size), identical to
+    `shard_chunks`."""
     n = len(frames_per_chunk)
     waves: List[List[Tuple[int, Tuple[int, ...]]]] = []
     nxt = 0
@@ -54,11 +67,7 @@ def plan_waves(frames_per_chunk: Sequence[int], world_size: int, allow_sp: bool 
         g = world_size // k
         wave = []
         for j in range(k):
-            gj = g
-            while frames_per_chunk[nxt + j] % gj:
-                gj -= 1
-                while g % gj:
-                    gj -= 1
+            gj = max(1, min(g, frames_per_chunk[nxt + j]))
             wave.append((nxt + j, tuple(range(j * g, j * g + gj))))
         waves.append(wave)
         nxt += k

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib, ops
 from .host.camera_estimation import camera_parameters_from_samples, sample_for_intrinsics
-from .host.datasets import ChunkImageDataset, plan_waves
+from .host.datasets import ChunkImageDataset, plan_waves, split_frames
 from .host.image_utils import calculate_target_size, load_images_u8, resize_u8_on_host
 from .host.keypoints import create_keypoint_extractor
 from .pi3 import Pi3
@@ -137,6 +137,7 @@ class OfflineChunkCreator:
         self.target_size: Optional[Tuple[int, int]] = None
         self.undistortion_maps = None
         self._sp_groups: Dict[Tuple[int, ...], object] = {}     # rank tuple -> process group of a sequence-parallel wave
+        self.last_run_stats: Dict = {}
         self._resize_tables: Dict[tuple, tuple] = {}            # (Hs, Ws, H, W) -> Pillow coefficient tables on the device
         if getattr(config, "cam_dist_path", None):
             print("⚠️  cam_dist_path given: undistortion maps (cv2/pytheia) are outside this build; ignoring")
@@ -218,31 +219,41 @@ class OfflineChunkCreator:
     def _process_chunk_sequence_parallel(self, frames_host: torch.Tensor, num_frames: int,
                                          chunk_paths: List, ranks: Tuple[int, ...], group) -> Optional[Dict]:
         """One chunk on a group of ranks (the tail waves of `plan_waves`): every rank runs the forward on its
-        contiguous slice of the frames with the chunk-global K/V all-gathered over NCCL (`Pi3.forward(sp_group=)`), the
+        contiguous slice of the frames (`split_frames`) with the chunk-global K/V all-gathered over NCCL
+        (`Pi3.forward(sp_group=)`: the local K/V block is attended to while the remote blocks are in flight), the
         per-frame outputs are all-gathered in frame order and the group's first rank does the post-processing and
-        returns the chunk dict (the other ranks return None). Outputs are bit-identical to the single-GPU forward.
+        returns the chunk dict (the other ranks return None). Outputs are within the bf16 tolerance of the single-GPU
+        forward (bit-identical with `model.sp_overlap = False` and an even split).
         `frames_host`: all `num_frames` frames on the group's first rank, this rank's slice on the others."""
         import torch.distributed as dist
         dev = self.config.device
         rank = dist.get_rank()
         g = len(ranks)
         li = ranks.index(rank)
-        n_loc = num_frames // g
+        split = split_frames(num_frames, g)
+        counts = [n for _, n in split]
+        n_max = max(counts)
         leader = li == 0
         with torch.no_grad():
             t0 = time.time()
             if leader:
                 imgs_dev = self._frames_to_device(frames_host)
-                local = imgs_dev[:, :n_loc]
+                local = imgs_dev[:, :counts[0]]
             else:
                 imgs_dev = None
                 local = self._frames_to_device(frames_host)
-            out = self.model(local.contiguous(), sp_group=group)
+            out = self.model(local.contiguous(), sp_group=group, sp_frame_counts=counts)
             full = {}
             for k in ("points", "local_points", "conf", "camera_poses"):
-                src = out[k][0].contiguous()
-                dst = torch.empty((num_frames,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
-                dist.all_gather_into_tensor(dst, src, group=group)
+                src = out[k][0]
+                if counts[li] < n_max:      # uneven split: blocks are padded to the largest rank's frame count
+                    pad = torch.zeros((n_max,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+                    pad[:counts[li]] = src
+                    src = pad
+                dst = torch.empty((g * n_max,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+                dist.all_gather_into_tensor(dst, src.contiguous(), group=group)
+                if leader and min(counts) < n_max:
+                    dst = torch.cat([dst[i * n_max:i * n_max + c] for i, c in enumerate(counts)])
                 full[k] = dst[None]
             torch.cuda.synchronize()
             dt_inf = max(1e-6, time.time() - t0)
@@ -375,6 +386,12 @@ class OfflineChunkCreator:
                     groups[ranks] = (torch.distributed.group.WORLD if len(ranks) == world
                                      else torch.distributed.new_group(ranks=list(ranks)))
         mine = [(ci, ranks) for wave in waves for ci, ranks in wave if rank in ranks]
+        wave_of = {ci: wi for wi, wave in enumerate(waves) for ci, _ in wave}
+        t_run0 = time.time()
+        # run statistics (bench.py reads them): when each of this rank's chunks was completely finished (saved, or for
+        # a non-leading sequence-parallel rank: its forward done), relative to the start of the run
+        self.last_run_stats = {"rank": rank, "world": world, "waves": [[(ci, list(rk)) for ci, rk in w] for w in waves],
+                               "chunk_done_s": {}, "chunk_wave": wave_of}
 
         saved_files: List[str] = []
         manifest: List[Dict] = []
@@ -392,8 +409,8 @@ class OfflineChunkCreator:
             b, e = dataset.chunk_indices[ci]
             li = rk.index(rank)
             if li > 0:
-                n_loc = (e - b) // len(rk)
-                b, e = b + li * n_loc, b + (li + 1) * n_loc
+                first, cnt = split_frames(e - b, len(rk))[li]
+                b, e = b + first, b + first + cnt
             # frames of one chunk are decoded by several threads, then gathered into one (pinned) buffer
             step = max(1, -(-(e - b) // frame_threads))
             parts = list(frame_pool.map(lambda lo: dataset.load_frames(lo, min(lo + step, e)), range(b, e, step)))
@@ -434,6 +451,7 @@ class OfflineChunkCreator:
                 print(f"   💾 Saved: {out_path}")
             except Exception as e:
                 print(f"❌ Failed to save chunk {chunk_idx}: {e}")
+            self.last_run_stats["chunk_done_s"][chunk_idx] = time.time() - t_run0
 
         # Software pipeline over this rank's whole-chunk jobs: the forward of chunk k+1 is enqueued (asynchronously)
         # before the host half of chunk k (intrinsics LM, dict assembly, torch.save) runs, so the GPU never waits for it.
@@ -471,6 +489,8 @@ class OfflineChunkCreator:
                     _t = time.time()
                     save(chunk_result, chunk_idx, chunk_paths)
                     t_save += time.time() - _t
+                else:
+                    self.last_run_stats["chunk_done_s"][chunk_idx] = time.time() - t_run0
                 continue
             num_frames = end_idx - start_idx
             with torch.no_grad():
@@ -492,6 +512,8 @@ class OfflineChunkCreator:
 
         pool.shutdown(wait=True)
         frame_pool.shutdown(wait=True)
+        self.last_run_stats.update(wait_frames_s=t_wait, enqueue_s=t_proc, host_half_s=t_save,
+                                   total_s=time.time() - t_run0)
         print(f"   host pipeline on rank {rank}: waited {t_wait:.3f}s for frames, {t_proc:.3f}s enqueueing chunks, "
               f"{t_save:.3f}s in the host half (wait for the GPU, intrinsics solve, save)")
         total_time = sum(infer_times)

@@ -74,6 +74,13 @@ class Pi3(nn.Module):
         # when set to a list, (start, end) CUDA events of every chunk-global attention launch are appended
         # (bench.py uses them for the live roofline of the dominant kernel)
         self.global_attn_events: Optional[list] = None
+        # sequence-parallel chunk-global layers: True = attend to the local K/V block while the remote blocks cross
+        # NVLink, then merge through the log-sum-exp (exposed all-gather ~0, result within bf16 tolerance of the
+        # single-GPU forward); False = blocking all-gather, one attention over all keys (bit-identical to one GPU)
+        self.sp_overlap: bool = True
+        # when set to a list, (local_done, gather_done) CUDA events of every sequence-parallel layer are appended:
+        # their distance is the all-gather time the local attention did not hide
+        self.sp_events: Optional[list] = None
 
     # ------------------------------------------------------------------ loading
     @classmethod
@@ -219,8 +226,8 @@ class Pi3(nn.Module):
         self._shape_cache[key] = c
         return c
 
-    def _buffers_for(self, BN: int, H: int, W: int, device: torch.device, sp_world: int = 1) -> dict:
-        key = (BN, H, W, str(device), sp_world)
+    def _buffers_for(self, BN: int, H: int, W: int, device: torch.device, sp_world: int = 1, sp_max_frames: int = 0) -> dict:
+        key = (BN, H, W, str(device), sp_world, sp_max_frames)
         a = self._arena.get(key)
         if a is not None:
             return a
@@ -239,27 +246,99 @@ class Pi3(nn.Module):
             "pooled": e(BN, 512), "pooled2": e(BN, 512), "rot9": e(BN, 12), "trans": e(BN, 4),
         }
         if sp_world > 1:
-            a["kv_send"] = e(M, 2 * D, dt=bf)
-            a["kv_all"] = e(sp_world * M, 2 * D, dt=bf)
+            m_max = max(sp_max_frames, BN) * T          # rows of the largest rank's block (uneven frame splits are padded)
+            a["kv_send"] = e(m_max, 2 * D, dt=bf)
+            a["kv_all"] = e(sp_world * m_max, 2 * D, dt=bf)
+            a["att_remote"] = e(M, D, dt=bf)
+            a["lse"] = e(2, HEADS, M)
         self._arena = {key: a}   # one live shape at a time
         return a
 
     # ------------------------------------------------------------------ forward
-    def _block(self, x, b, bufs, num_seqs, seq_len, T, pw, cs, rope: bool, sp_group=None) -> None:
+    @staticmethod
+    def _sp_plan(group, frame_counts, T: int) -> dict:
+        """Per-forward constants of the sequence-parallel chunk-global layers. Every rank's K|V block lands at
+        offset g * m_max of the gathered buffer (blocks of ranks with fewer frames are padded). Softmax attention does
+        not care about the ORDER of the keys, so the remote rows are made contiguous by moving rows from the end of the
+        buffer into the holes (this rank's own block, pad rows): `copies` = (dst, src, n) row ranges."""
+        import torch.distributed as dist
+        G = dist.get_world_size(group)
+        r = dist.get_rank(group)
+        rows = [int(c) * T for c in frame_counts]
+        m_max = max(rows)
+        valid = [(g * m_max, rows[g]) for g in range(G) if g != r and rows[g] > 0]
+        R = sum(n for _, n in valid)
+        holes, movers, pos = [], [], 0
+        for s0, n in valid:
+            lo, hi = s0, s0 + n
+            if lo >= R:
+                movers.append((lo, n))
+                continue
+            if lo > pos:
+                holes.append((pos, lo - pos))
+            if hi > R:
+                movers.append((R, hi - R))
+                hi = R
+            pos = hi
+        if pos < R:
+            holes.append((pos, R - pos))
+        copies = []
+        movers = movers[::-1]
+        for dst, need in holes:
+            while need > 0:
+                src, have = movers[-1]
+                n = min(need, have)
+                copies.append((dst, src + have - n, n))       # take from the end of the mover
+                if n == have:
+                    movers.pop()
+                else:
+                    movers[-1] = (src, have - n)
+                dst += n
+                need -= n
+        assert not movers
+        return dict(group=group, G=G, rank=r, rows=rows, m_max=m_max, remote_rows=R, copies=copies,
+                    all_rows=sum(rows), equal=len(set(rows)) == 1)
+
+    def _sp_global_attention(self, qkv, att, bufs, sp: dict, M: int) -> None:
+        """Chunk-global attention of the M local query rows against the K/V rows of every rank of the group
+        (`att` = softmax(q K^T / 8) V over all sum(rows) keys). K|V cross NVLink as one NCCL all-gather per layer."""
+        import torch.distributed as dist
+        kv_send, kv_all = bufs["kv_send"], bufs["kv_all"]
+        kv_send[:M].copy_(qkv[:, D:])                     # k | v of the local frames, made contiguous
+        if not self.sp_overlap:
+            # blocking variant: one attention over the gathered keys in frame order (bit-identical to a single GPU);
+            # needs equal blocks so that the gathered buffer has no pad rows inside the sequence
+            if not sp["equal"]:
+                raise ValueError("sp_overlap=False needs the same number of frames on every rank")
+            dist.all_gather_into_tensor(kv_all, kv_send, group=sp["group"])
+            ops.attention_q_kv(qkv, kv_all, att, 1, M, sp["all_rows"], HEADS, 0.125)
+            return
+        work = dist.all_gather_into_tensor(kv_all, kv_send, group=sp["group"], async_op=True)   # NCCL's own stream
+        lse = bufs["lse"]
+        ops.attention_q_kv_lse(qkv, kv_send[:M], att, lse[0], 1, M, M, HEADS, 0.125)             # local block meanwhile
+        if self.sp_events is not None:
+            e0 = torch.cuda.Event(enable_timing=True); e0.record()
+        work.wait()                                       # the current stream waits for the gathered rows
+        if self.sp_events is not None:
+            e1 = torch.cuda.Event(enable_timing=True); e1.record()
+            self.sp_events.append((e0, e1))
+        for dst, src, n in sp["copies"]:
+            kv_all[dst:dst + n].copy_(kv_all[src:src + n])
+        R = sp["remote_rows"]
+        ops.attention_q_kv_lse(qkv, kv_all[:R], bufs["att_remote"], lse[1], 1, M, R, HEADS, 0.125)
+        ops.attention_merge([att, bufs["att_remote"]], [lse[0], lse[1]], att, HEADS)
+
+    def _block(self, x, b, bufs, num_seqs, seq_len, T, pw, cs, rope: bool, sp=None) -> None:
         """x += ls1 * proj(attn(LN(x)));  x += ls2 * fc2(GELU(fc1(LN(x))))   (block.py:333-334), in place on x.
-        With `sp_group` (sequence-parallel chunk-global layer) the local queries attend to the K/V rows of every
-        rank of the group, all-gathered over NCCL in frame order."""
+        With `sp` (sequence-parallel chunk-global layer, see `_sp_plan`) the local queries attend to the K/V rows of
+        every rank of the group, all-gathered over NCCL."""
         h, qkv, att, mlp = bufs["h"], bufs["qkv"], bufs["att"], bufs["mlp"]
         ops.layernorm(x, b["n1"][0], b["n1"][1], 1e-6, h)
         ops.gemm(h, b["qkv_w"], qkv, bias=b["qkv_b"])
         if rope or b["qn"] is not None:
             ops.qknorm_rope(qkv, HEADS, T, N_SPECIAL, pw, cs if rope else None, b["qn"], b["kn"], 1e-5)
-        if sp_group is not None:
-            import torch.distributed as dist
-            G = dist.get_world_size(sp_group)
-            bufs["kv_send"].copy_(qkv[:, D:])                     # k | v of the local frames, made contiguous
-            dist.all_gather_into_tensor(bufs["kv_all"], bufs["kv_send"], group=sp_group)
-            ops.attention_q_kv(qkv, bufs["kv_all"], att, 1, seq_len, G * seq_len, HEADS, 0.125)
+        if sp is not None:
+            self._sp_global_attention(qkv, att, bufs, sp, seq_len)
         elif self.global_attn_events is not None and seq_len != T:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -274,11 +353,13 @@ class Pi3(nn.Module):
         ops.gemm(mlp, b["fc2_w"], x, bias=b["fc2_b"], gamma=b["ls2"], resid=x)
 
     @torch.no_grad()
-    def forward(self, imgs: torch.Tensor, taps: Optional[dict] = None, sp_group=None) -> Dict[str, torch.Tensor]:
+    def forward(self, imgs: torch.Tensor, taps: Optional[dict] = None, sp_group=None,
+                sp_frame_counts=None) -> Dict[str, torch.Tensor]:
         """Reference signature `forward(imgs)`. Extension for over-long chunks: with `sp_group` (a
-        torch.distributed group, NCCL) `imgs` holds this rank's contiguous, equally sized slice of the chunk's
-        frames (rank order = frame order, B = 1); frame-local layers, MLPs and heads run locally, each of the 18
-        chunk-global layers all-gathers bf16 K and V across the group. Returns the local frames' outputs."""
+        torch.distributed group, NCCL) `imgs` holds this rank's contiguous slice of the chunk's frames (rank order =
+        frame order, B = 1); frame-local layers, MLPs and heads run locally, each of the 18 chunk-global layers
+        all-gathers bf16 K and V across the group. `sp_frame_counts`: frames held by each rank of the group (default:
+        the same number everywhere). Returns the local frames' outputs."""
         if imgs.dim() != 5 or imgs.shape[2] != 3:
             raise ValueError("imgs must be (B, N, 3, H, W)")
         sp_world = 1
@@ -296,9 +377,9 @@ class Pi3(nn.Module):
             raise ValueError("H and W must be multiples of 14")
         # the C ABI launches on the CURRENT device and stream: make the frames' device current for the whole schedule
         with ops.on_device_of(imgs):
-            return self._forward_on_device(imgs, taps, sp_group, sp_world)
+            return self._forward_on_device(imgs, taps, sp_group, sp_world, sp_frame_counts)
 
-    def _forward_on_device(self, imgs, taps, sp_group, sp_world) -> Dict[str, torch.Tensor]:
+    def _forward_on_device(self, imgs, taps, sp_group, sp_world, sp_frame_counts) -> Dict[str, torch.Tensor]:
         B, N, _, H, W = imgs.shape
         device = imgs.device
         pk = self._pack(device)
@@ -308,7 +389,15 @@ class Pi3(nn.Module):
         T = P + N_SPECIAL
         BN = B * N
         M = BN * T
-        bufs = self._buffers_for(BN, H, W, device, sp_world)
+        sp = None
+        if sp_group is not None:
+            counts = list(sp_frame_counts) if sp_frame_counts is not None else [N] * sp_world
+            if len(counts) != sp_world:
+                raise ValueError("sp_frame_counts must have one entry per rank of sp_group")
+            sp = self._sp_plan(sp_group, counts, T)
+            if sp["rows"][sp["rank"]] != M:
+                raise ValueError("sp_frame_counts disagrees with the number of local frames")
+        bufs = self._buffers_for(BN, H, W, device, sp_world, max(sp_frame_counts) if sp_frame_counts is not None else 0)
         x = bufs["x"]
         imgs_f = imgs.reshape(BN, 3, H, W).to(torch.float32).contiguous()
 
@@ -333,7 +422,7 @@ class Pi3(nn.Module):
             if i % 2 == 0:
                 self._block(x, b, bufs, BN, T, T, pw, sc["cs"], rope=True)
             else:
-                self._block(x, b, bufs, B, N * T, T, pw, sc["cs"], rope=True, sp_group=sp_group)
+                self._block(x, b, bufs, B, N * T, T, pw, sc["cs"], rope=True, sp=sp)
             if taps is not None and i in (0, 1):
                 taps[f"dec_block{i}"] = x.view(BN, T, D).clone()
             if i == 34:

@@ -40,18 +40,24 @@ def main():
     libs = sorted(glob.glob(os.path.join(ROOT, "pi3_slam_b200/build/variants/*.so")))
     if only:
         libs = [l for l in libs if os.path.basename(l)[:-3] in only.split(",")]
+    # ENVS="name:K=V,K2=V2;name2:..." runs each library once more per named environment (e.g. PI3B_ATTN_TAIL=0)
+    envsets = [("", {})]
+    for spec in filter(None, os.environ.get("ENVS", "").split(";")):
+        nm, kv = spec.split(":", 1)
+        envsets.append(("@" + nm, dict(x.split("=", 1) for x in kv.split(","))))
+    libs = [(l, sfx, ev) for l in libs for sfx, ev in envsets]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "ab_attn.log"), "a") as log:
         for rep in range(reps):
-            for lib in libs:
-                env = dict(os.environ, PI3B_LIB=lib)
+            for lib, sfx, extra_env in libs:
+                env = dict(os.environ, PI3B_LIB=lib, **extra_env)
                 code = CHILD % dict(root=ROOT, check=1 if rep == 0 else 0)
                 try:
                     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=180)
                     line = r.stdout.split("RES", 1)[1].strip() if "RES" in r.stdout else "FAILED " + r.stderr[-400:]
                 except subprocess.TimeoutExpired:
                     line = "TIMEOUT"
-                msg = f"rep {rep} {os.path.basename(lib)[:-3]:12s} {line}"
+                msg = f"rep {rep} {os.path.basename(lib)[:-3] + sfx:18s} {line}"
                 print(msg, flush=True)
                 log.write(msg + "\n"); log.flush()
 

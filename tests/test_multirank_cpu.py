@@ -55,7 +55,7 @@ def test_plan_waves_properties():
         for w in waves:
             used = [r for _, ranks in w for r in ranks]
             assert len(used) == len(set(used)) and all(0 <= r < world for r in used)
-            assert all(frames[c] % len(ranks) == 0 for c, ranks in w)
+            assert all(len(ranks) <= frames[c] for c, ranks in w)
         # plain sharding when sequence parallelism is off
         flat = plan_waves(frames, world, allow_sp=False)
         for r in range(world):
@@ -65,5 +65,10 @@ def test_plan_waves_properties():
     # makespan in chunk-times (cost ~ frames^2 for the dominant global attention; SP divides it by the group size)
     cost = lambda wv: max((frames[c] / 100) ** 2 / len(r) for c, r in wv)          # noqa: E731
     assert sum(cost(w) for w in w8) < 1.53 and sum(cost(w) for w in plan_waves(frames, 8, False)) == 2.0
-    # a chunk whose frame count does not divide falls back to a smaller group
-    assert plan_waves([100] * 5 + [37], 4)[-1] == [(4, (0, 1)), (5, (2,))]
+    # a frame count that does not divide is split unevenly (19 + 18 frames), the group keeps its size
+    from pi3_slam_b200.host.datasets import split_frames
+    assert plan_waves([100] * 5 + [37], 4)[-1] == [(4, (0, 1)), (5, (2, 3))]
+    assert split_frames(37, 2) == [(0, 19), (19, 18)] and split_frames(300, 8)[3:5] == [(114, 38), (152, 37)]
+    assert sum(n for _, n in split_frames(300, 8)) == 300 and split_frames(3, 2) == [(0, 2), (2, 1)]
+    # fewer frames than ranks: the group shrinks
+    assert plan_waves([2], 4) == [[(0, (0, 1))]]
