@@ -11,7 +11,16 @@ by torch.distributed.run, one rank per GPU) every rank runs its own chunk — ch
 no data-path collective — and `value` is total frames over the max-over-ranks device time ("weak" scaling).
 
 `--impl reference` times the reference's CPU algorithm (the oracle port: /root/reference is a Python package
-that does not exist on the GPU box) on the host cores, on a bounded sample of the same workload.
+that does not exist on the GPU box) on the host cores, on a bounded sample of the same workload (8 frames of the
+workload's resolution).
+
+Outside the timed regions the line also carries
+  parity        the timed step's outputs against the oracle evaluated on the GPU in strict fp32 (N = 1 only);
+  cpu_baseline  the 8-frame CPU sample and one SAME-WORK pair (cfg1, 8 x 224 x 224, in full on both sides);
+  extra.cfg3_sequence   `process_and_save` on the 1000-frame 308x406 synthetic sequence under the hybrid schedule
+                        (whole chunks per rank, last waves sequence-parallel): makespan, frames/s, per-wave split;
+  extra.cfg5_sp         (N >= 2) one 300-frame chunk, sequence-parallel over all N ranks: ms/chunk, all-gather
+                        ms/layer and how much of it the local-block attention did not hide.
 """
 from __future__ import annotations
 
@@ -32,7 +41,7 @@ WORKLOADS = {
     "cfg2": (100, 378, 518, "BASELINE configs[1]: one 100-frame chunk at 378x518 (P=999, T=1004, 100400 tokens)"),
     "cfg3": (100, 308, 406, "BASELINE configs[2] chunk shape: 100 frames at 308x406 (640x480 source), 64300 tokens"),
 }
-CPU_SAMPLE_FRAMES = 2
+CPU_SAMPLE_FRAMES = 8
 
 
 def _peaks():
@@ -116,6 +125,254 @@ def cpu_reference_run(frames: int, H: int, W: int, steps: int, warmup: int, sd=N
             "s_per_step": dt}
 
 
+def parity_block(model, dev_frames, out, sd) -> dict:
+    """Outputs of the timed step against the oracle evaluated on the same GPU in strict fp32 (TF32 off), same inputs,
+    same weights, the whole chunk (chunk-global attention couples every frame). Outside the timed region."""
+    import torch
+    from oracle import pi3_oracle
+    t0 = time.perf_counter()
+    mine = {k: v.clone() for k, v in out.items()}
+    model._invalidate()                       # release the engine's arena and packed weights while the oracle runs
+    torch.cuda.empty_cache()
+    ref = pi3_oracle.pi3_forward_gpu_fp32(dev_frames, sd, device=dev_frames.device)
+    res = {k: pi3_oracle.rel_l2(mine[k], ref[k]) for k in ("points", "local_points", "conf")}
+    res["rot_rad"], res["rel_t"] = pi3_oracle.pose_errors(mine["camera_poses"].cpu(), ref["camera_poses"].cpu())
+    tol = dict(points=1e-2, local_points=1e-2, conf=2e-2, rot_rad=1e-3, rel_t=1e-3)
+    del ref, mine
+    torch.cuda.empty_cache()
+    return {"against": "oracle.pi3_oracle.pi3_forward on the same GPU, fp32, TF32 off, all frames of the timed chunk",
+            "errors": res, "tolerance": tol, "within_tolerance": all(res[k] < tol[k] for k in tol),
+            "seconds": time.perf_counter() - t0}
+
+
+def same_work_pair(model, sd, dev) -> dict:
+    """cfg1 (BASELINE configs[0], 8 x 224 x 224) in full on both sides: the one GPU/CPU ratio that compares equal work."""
+    import torch
+    from pi3_slam_b200.synthetic import make_frames
+    frames, H, W, _ = WORKLOADS["cfg1"]
+    host = make_frames(frames, H, W)[None].pin_memory()
+    host_out = None
+    for _ in range(3):
+        o = model(host.to(dev, non_blocking=True))
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()}
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        o = model(host.to(dev, non_blocking=True))
+        for k, v in o.items():
+            host_out[k].copy_(v, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gpu_ms = e0.elapsed_time(e1) / n
+    cpu = cpu_reference_run(frames, H, W, 1, 0, sd)
+    return {"workload": "cfg1: 8 frames at 224x224 (2088 tokens), whole chunk on both sides, host frames to host results",
+            "gpu_frames_per_s": frames / (gpu_ms * 1e-3), "gpu_ms": gpu_ms, "cpu_frames_per_s": cpu["value"],
+            "cpu_s": cpu["s_per_step"], "cpu_cores": cpu["cores"], "ratio": frames / (gpu_ms * 1e-3) / cpu["value"]}
+
+
+def gemm_roofline(dev, peaks) -> dict:
+    """The four trunk GEMM shapes of the workload (qkv, proj + LayerScale + residual, fc1 + GELU, fc2 + LayerScale +
+    residual at M = 100 400), each timed alone with CUDA events (burst conditions), next to cuBLAS on the same box."""
+    import torch
+    from pi3_slam_b200 import ops
+    M = 100400
+    shapes = [("qkv", 3072, 1024, 0, False), ("proj_ls_resid", 1024, 1024, 0, True), ("fc1_gelu", 4096, 1024, 1, False),
+              ("fc2_ls_resid", 1024, 4096, 0, True)]
+    rows = []
+    for name, N, K, act, resid in shapes:
+        a = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) * 0.02).bfloat16()
+        b = torch.randn(N, device=dev)
+        if resid:
+            g = torch.rand(N, device=dev)
+            x = torch.randn(M, N, device=dev)
+            fn = lambda: ops.gemm(a, w, x, bias=b, gamma=g, resid=x)                      # noqa: E731
+        else:
+            o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            fn = lambda: ops.gemm(a, w, o, bias=b, act=act)                               # noqa: E731
+        bb = b.bfloat16()
+        ref = lambda: torch.nn.functional.linear(a, w, bb)                                # noqa: E731
+        ts = []
+        for f in (fn, ref):
+            for _ in range(3):
+                f()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                f()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / 10)
+        fl = 2.0 * M * N * K
+        rows.append({"shape": name, "M": M, "N": N, "K": K, "ms": ts[0], "tflops": fl / ts[0] / 1e9,
+                     "cublas_plain_ms": ts[1], "cublas_plain_tflops": fl / ts[1] / 1e9,
+                     "frac_of_burst_peak": fl / ts[0] / 1e9 / peaks["burst"]})
+        del a, w
+    tot_fl = sum(2.0 * r["M"] * r["N"] * r["K"] for r in rows)
+    tot_ms = sum(r["ms"] for r in rows)
+    prof = None
+    ppath = os.path.join(ROOT, "profiles", "gemm_tensor_pipe.json")
+    if os.path.exists(ppath):
+        with open(ppath) as f:
+            prof = json.load(f)
+    return {"kernel": "gemm_kernel (tcgen05, fused epilogues), the four trunk shapes of one block", "bound": "tensor",
+            "achieved": tot_fl / tot_ms / 1e9, "peak": peaks["burst"], "unit": "TFLOP/s",
+            "frac": tot_fl / tot_ms / 1e9 / peaks["burst"],
+            "peak_source": f"{peaks['source']} (burst figure: kernels timed alone); cuBLAS column = torch linear "
+                           f"without the fused GELU / LayerScale / residual",
+            "shapes": rows, "ncu_tensor_pipe": prof}
+
+
+def cfg3_sequence_extra(model, dev, rank, world) -> dict:
+    """BASELINE configs[2]: the whole offline chunk creation (frames -> forward -> masks, keypoints, intrinsics ->
+    chunk files) on a 1000-frame 640x480-shaped synthetic sequence (target 308x406), chunk 100 / overlap 20 = 13
+    chunks, scheduled over the ranks by plan_waves (hybrid: the last waves run sequence-parallel)."""
+    import shutil
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from pi3_slam_b200.offline_chunk_creator import OfflineChunkCreator, OfflineCreatorConfig
+    from pi3_slam_b200.synthetic import make_frames
+    frames, H, W = 1000, 308, 406
+    paths = [f"/synthetic/{i:05d}.png" for i in range(frames)]
+    index = {p: i for i, p in enumerate(paths)}
+    loader = lambda ps, ts: torch.cat([make_frames(1, *ts, start_index=index[p]) for p in ps])  # noqa: E731
+    box = [tempfile.mkdtemp(prefix="pi3b_cfg3_")]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    root = box[0]
+    cfg = OfflineCreatorConfig(model_path="unused", output_dir=root, device=str(dev), do_metric_depth=False,
+                               keypoint_type="grid", max_num_keypoints=200, chunk_length=100, overlap=20, keypoint_seed=5,
+                               sequence_parallel_tail=True)
+    cr = OfflineChunkCreator(cfg, model=model)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    devnull = open(os.devnull, "w")
+    saved = sys.stdout
+    sys.stdout = devnull                          # the creator prints per-chunk progress like the reference
+    try:
+        warm = paths[:180] if world == 1 else paths   # warm-up: allocations, NCCL groups of the sequence-parallel waves
+        cr.process_and_save(warm, loader=loader, target_size=(H, W))
+        sync()
+        t0 = time.perf_counter()
+        cr.process_and_save(paths, loader=loader, target_size=(H, W))
+        sync()
+        makespan = time.perf_counter() - t0
+    finally:
+        sys.stdout = saved
+        devnull.close()
+    st = cr.last_run_stats
+    stats = [st]
+    if world > 1:
+        stats = [None] * world
+        dist.all_gather_object(stats, st)
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+    t = torch.tensor([makespan], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    makespan = float(t.item())
+    waves = st["waves"]
+    wave_done = []
+    for wi, wave in enumerate(waves):
+        done = [s["chunk_done_s"].get(ci) for s in stats for ci, _ in wave if s["chunk_done_s"].get(ci) is not None]
+        wave_done.append(max(done) if done else None)
+    processed = sum(min(100, frames - 80 * i) for i in range(13))
+    return {"workload": "cfg3: 1000 frames 308x406, chunk 100 / overlap 20 (13 chunks, 1240 processed frames), grid "
+                        "keypoints 200, intrinsics solve, chunk files written", "n_gpus": world,
+            "makespan_s": makespan, "sequence_frames_per_s": frames / makespan,
+            "processed_frames_per_s": processed / makespan,
+            "waves": [[len(r) for _, r in w] for w in waves], "wave_done_s": wave_done,
+            "rank0_host_split_s": {k: st[k] for k in ("wait_frames_s", "enqueue_s", "host_half_s", "total_s")},
+            "slowest_rank_host_half_s": max(s["host_half_s"] for s in stats)}
+
+
+def cfg5_sp_extra(model, dev, rank, world) -> dict:
+    """BASELINE configs[4]: one 300-frame 308x406 chunk (192 900 tokens), sequence-parallel over all ranks: per-rank
+    frames as even as possible, K|V all-gathered over NVLink in each of the 18 chunk-global layers, overlapped with the
+    attention over the local block."""
+    import torch
+    import torch.distributed as dist
+    from pi3_slam_b200.host.datasets import split_frames
+    from pi3_slam_b200.pi3 import Pi3
+    from pi3_slam_b200.synthetic import make_frames
+    frames, H, W = 300, 308, 406
+    T = (H // 14) * (W // 14) + 5
+    split = split_frames(frames, world)
+    first, cnt = split[rank]
+    counts = [n for _, n in split]
+    fr = make_frames(cnt, H, W, start_index=first)[None].to(dev)
+    res = {"workload": "cfg5: one 300-frame chunk at 308x406 (192 900 tokens)", "n_gpus": world, "frames_per_rank": counts}
+
+    def run(steps):
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            model(fr, sp_group=dist.group.WORLD, sp_frame_counts=counts)
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    run(1)
+    model.sp_events = []
+    ms = run(2)
+    exposed = [a.elapsed_time(b) for a, b in model.sp_events]
+    model.sp_events = None
+    model.sp_overlap = False
+    ms_blocking = run(1) if len(set(counts)) == 1 else None       # the blocking variant needs an even split
+    model.sp_overlap = True
+    # the all-gather alone
+    m_max = max(counts) * T
+    send = torch.empty(m_max, 2048, device=dev, dtype=torch.bfloat16)
+    recv = torch.empty(world * m_max, 2048, device=dev, dtype=torch.bfloat16)
+    for _ in range(2):
+        dist.all_gather_into_tensor(recv, send)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        dist.all_gather_into_tensor(recv, send)
+    e1.record()
+    torch.cuda.synchronize()
+    ag_ms = e0.elapsed_time(e1) / 5
+    fl = Pi3.flops(frames, H, W)
+    ex = torch.tensor([sum(exposed) / max(1, len(exposed))], device=dev, dtype=torch.float64)
+    dist.all_reduce(ex, op=dist.ReduceOp.MAX)
+    layer_ms = (fl["global_attn"] / 18 / world) / 1e9 / 900.0     # a global layer's attention at ~900 TFLOP/s per GPU
+    res.update(ms_per_chunk=ms, frames_per_s=frames / (ms * 1e-3),
+               tflops_per_gpu=fl["total"] / (ms * 1e-3) / 1e12 / world, ms_per_chunk_blocking_allgather=ms_blocking,
+               allgather_ms_per_layer=ag_ms,
+               allgather_recv_bytes_per_rank_per_layer=(world - 1) * m_max * 4096,
+               allgather_gbs_per_rank=(world - 1) * m_max * 4096 / (ag_ms * 1e-3) / 1e9,
+               exposed_allgather_ms_per_layer=float(ex.item()),
+               exposed_share_of_global_layer=float(ex.item()) / (layer_ms + float(ex.item())))
+    # correctness on a small shape: blocking variant bit-identical to the single-GPU forward, overlapped within tolerance
+    n_small = 2 * world
+    small = make_frames(n_small, 56, 84)[None].to(dev)
+    ref = {k: v[:, 2 * rank:2 * rank + 2].clone() for k, v in model(small).items()}
+    model.sp_overlap = False
+    o1 = model(small[:, 2 * rank:2 * rank + 2].contiguous(), sp_group=dist.group.WORLD)
+    same = all(torch.equal(o1[k], ref[k]) for k in ref)
+    model.sp_overlap = True
+    o2 = model(small[:, 2 * rank:2 * rank + 2].contiguous(), sp_group=dist.group.WORLD)
+    err = max(float((o2[k].double() - ref[k].double()).norm() / ref[k].double().norm()) for k in ref)
+    flag = torch.tensor([1.0 if same else 0.0, -err], device=dev, dtype=torch.float64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["small_shape_blocking_bit_identical_to_1gpu"] = bool(flag[0].item() == 1.0)
+    res["small_shape_overlapped_max_rel_l2"] = -float(flag[1].item())
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -124,6 +381,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the GPU-fp32 oracle comparison of the timed step")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra.cfg3_sequence / extra.cfg5_sp / roofline.gemm")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: until it is emitted fd 1 points at stderr, so native writers (the NCCL
     # version banner is a printf to stdout, whatever NCCL_DEBUG_FILE says) cannot interleave with it
@@ -149,7 +408,7 @@ def main():
         if rank != 0:
             return
         import torch
-        steps = max(1, min(args.steps, 3))
+        steps = max(1, min(args.steps, 2))        # ~12 s per 8-frame step: the whole arm stays within a minute
         r = cpu_reference_run(CPU_SAMPLE_FRAMES, H, W, steps, min(args.warmup, 1))
         line = {"impl": "reference", "metric": "pi3_chunk_frames_per_sec", "value": r["value"], "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["s_per_step"] * 1e3,
@@ -237,6 +496,27 @@ def main():
     e2e_ms_step = float(t2.item()) / args.steps
     finite = all(bool(torch.isfinite(v).all()) for v in host_out.values())
 
+    # ---- outside the timed regions -------------------------------------------------------------------------------
+    def guarded(fn, *a):
+        try:
+            return fn(*a)
+        except Exception as e:          # an extra must never cost the headline line
+            import traceback
+            traceback.print_exc()
+            return {"error": f"{type(e).__name__}: {e}"}
+
+    extra = {}
+    gemm_entry = None
+    if not args.no_extras and args.workload == "cfg2":
+        extra["cfg3_sequence"] = guarded(cfg3_sequence_extra, model, dev, rank, world)
+        if world > 1:
+            extra["cfg5_sp"] = guarded(cfg5_sp_extra, model, dev, rank, world)
+        if rank == 0:
+            gemm_entry = guarded(gemm_roofline, dev, _peaks())
+    parity = None
+    if rank == 0 and world == 1 and not args.no_parity:
+        parity = guarded(parity_block, model, dev_frames, out, sd)
+
     if rank == 0:
         fl = Pi3.flops(frames, H, W)
         peaks = _peaks()
@@ -265,7 +545,7 @@ def main():
             "frac_of_bf16_peak": {"burst": fl["total"] / (ms_step * 1e-3) / 1e12 / peaks["burst"],
                                   "sustained": fl["total"] / (ms_step * 1e-3) / 1e12 / peaks["sustained"],
                                   "note": "per-GPU achieved / per-GPU measured peak"},
-            "roofline": {"kernel": "attn_fwd_kernel (chunk-global attention, 18 launches/step)", "bound": "tensor",
+            "roofline": {"kernel": "attn_fwd_kernel_t3 (chunk-global attention, 18 launches/step)", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["sustained"]) if achieved else None,
                          "frac_of_burst_peak": (achieved / peaks["burst"]) if achieved else None,
@@ -274,9 +554,17 @@ def main():
                          "share_of_step": (sum(attn_ms) / args.steps) / ms_step if attn_ms else None,
                          "traffic": traffic, "traffic_detail": traffic_detail},
         }
+        line["parity"] = parity
+        if gemm_entry is not None:
+            line["roofline"]["gemm"] = gemm_entry
+        if extra:
+            line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(CPU_SAMPLE_FRAMES, H, W, 1, 0, sd)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["same_work"] = guarded(same_work_pair, model, sd, dev)
+            if "ratio" in line["cpu_baseline"]["same_work"]:
+                line["cpu_baseline"]["same_work_ratio"] = line["cpu_baseline"]["same_work"]["ratio"]
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -1,14 +1,36 @@
-"""Tiny driver for ncu: a few launches of one GEMM shape."""
-import sys, os
+"""Driver for ncu: one launch of each trunk GEMM shape of the cfg2 chunk (qkv, proj + LayerScale + residual, fc1 + GELU,
+fc2 + LayerScale + residual at M = 100 400) through pi3b_gemm, followed by the cuBLAS (torch linear) kernels of the same
+shapes for comparison. `python scripts/prof_gemm.py [reps]`."""
+import os
+import sys
+
 import torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pi3_slam_b200 import ops
-M, N, K, act = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-a = torch.randn(M, K, device="cuda").bfloat16()
-w = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
-b = torch.randn(N, device="cuda")
-out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-for _ in range(3):
-    ops.gemm(a, w, out, bias=b, act=act)
+from pi3_slam_b200 import ops  # noqa: E402
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+M = 100400
+dev = "cuda"
+ours, ref = [], []
+for name, N, K, act, resid in [("qkv", 3072, 1024, 0, False), ("proj", 1024, 1024, 0, True), ("fc1", 4096, 1024, 1, False),
+                               ("fc2", 1024, 4096, 0, True)]:
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.02).bfloat16()
+    b = torch.randn(N, device=dev)
+    bb = b.bfloat16()
+    if resid:
+        g = torch.rand(N, device=dev)
+        x = torch.randn(M, N, device=dev)
+        ours.append(lambda a=a, w=w, b=b, g=g, x=x: ops.gemm(a, w, x, bias=b, gamma=g, resid=x))
+    else:
+        o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ours.append(lambda a=a, w=w, b=b, o=o, act=act: ops.gemm(a, w, o, bias=b, act=act))
+    ref.append(lambda a=a, w=w, bb=bb: torch.nn.functional.linear(a, w, bb))
+for _ in range(reps):
+    for f in ours:
+        f()
+    for f in ref:
+        f()
 torch.cuda.synchronize()
 print("ok")
