@@ -39,6 +39,18 @@ int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda, const void
               const float* bias, const float* gamma, const float* resid, int64_t ld_resid, void* out, int64_t ldo,
               int out_f32, int act, int grp_in, int grp_out, int grp_off);
 
+/* The QKV projection with the q/k post-processing fused into the epilogue: out[M, 3*64*num_heads] bf16 =
+ * (A[M,K] * W[3*64*num_heads, K]^T + bias) rounded to bf16, then on every 64-channel head of the q and k thirds
+ * LayerNorm(64) (qk_norm = fp32 [4][64]: q weight, q bias, k weight, k bias; NULL to skip) and 2-D RoPE (cs_table fp32
+ * [table_rows][16][2] = (cos, sin) of pos * base^(-j/16); NULL to skip; token geometry as pi3b_qknorm_rope); the v third
+ * is stored as is. Bit-identical to pi3b_gemm followed by pi3b_qknorm_rope, without that pass's read-modify-write of the
+ * q and k thirds (822 MB per layer at 100 400 tokens). A, W bf16.
+ * replaces: qkv Linear + q_norm / k_norm + rope of pi3/models/layers/attention.py:326-334 in one launch; supersedes the
+ *   reference's native rope_2d_cuda_kernel (pi3/models/curope/kernels.cu:17-108), which is a separate in-place pass. */
+int pi3b_gemm_qkv(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int num_heads, int K,
+                  const float* bias, void* out, int64_t ldo, const float* qk_norm, float eps, const float* cs_table,
+                  int table_rows, int tokens_per_frame, int n_special, int patch_w);
+
 /* out = softmax(q k^T * scale) v, head_dim 64, bf16, per (sequence, head). Sequence s owns query / output rows
  * [s*q_len, (s+1)*q_len) and key / value rows [s*kv_len, (s+1)*kv_len) (q_len != kv_len: the sequence-parallel case,
  * local queries against all-gathered K/V); head h lives at columns {q,k,v}_col0 + 64*h of its operand; out at 64*h.

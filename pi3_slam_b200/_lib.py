@@ -23,6 +23,9 @@ SIGNATURES = {
     # stream, in_dtype, A, lda, W, ldw, M, N, K, bias, gamma, resid, ld_resid, out, ldo, out_f32, act, grp_in, grp_out, grp_off
     "pi3b_gemm": (c_int, [_P, c_int, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, _P,
                           c_int64, c_int, c_int, c_int, c_int, c_int]),
+    # stream, A, lda, W, ldw, M, num_heads, K, bias, out, ldo, qk_norm, eps, cs_table, table_rows, tokens_per_frame, n_special, patch_w
+    "pi3b_gemm_qkv": (c_int, [_P, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, c_int64, _P, c_float, _P, c_int,
+                              c_int, c_int, c_int]),
     # stream, q, k, v, ldq, ldk, ldv, q_col0, k_col0, v_col0, out, ldo, num_seqs, q_len, kv_len, num_heads, scale
     "pi3b_attn_fwd_hd64": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64,
                                    c_int, c_int, c_int, c_int, c_float]),

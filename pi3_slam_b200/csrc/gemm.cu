@@ -15,6 +15,7 @@
 
 #include "host_common.h"
 #include "ptx.cuh"
+#include "qk_math.cuh"
 
 namespace pi3b {
 
@@ -31,6 +32,14 @@ struct GemmParams {
   // output-row remap: GEMM row m lands in row (m / grp_in) * grp_out + grp_off + m % grp_in of out/resid
   // (grp_in == 0: identity). Used to scatter patch rows between the per-frame special tokens.
   int grp_in, grp_out, grp_off;
+  // fused QKV epilogue (pi3b_gemm_qkv): columns [0, qk_cols) are the q then the k heads (64 channels each, qk_cols / 2
+  // per third), the rest (v) is stored as is. qk_mode bit 0: LayerNorm(64) with qk_norm = fp32 [4][64] (q weight, q bias,
+  // k weight, k bias); bit 1: RoPE-2D with cs_table fp32 [pos][16] (cos, sin) and the token geometry below.
+  int qk_mode, qk_cols;
+  const float* qk_norm;
+  const float2* cs_table;
+  float qk_eps;
+  int tokens_per_frame, n_special, patch_w;
 };
 
 constexpr int kBlockM = 128;
@@ -50,7 +59,9 @@ struct GemmSmem {
   // per-epilogue-warp copy of the bias / gamma slice of the current tile (fetched while the main loop runs)
   static constexpr int BG_OFFSET = STG_OFFSET + kNumEpiWarps * STG_BYTES_PER_WARP;
   static constexpr int BG_BYTES_PER_WARP = 2 * (BLOCK_N / 2) * 4;
-  static constexpr int BAR_OFFSET = BG_OFFSET + kNumEpiWarps * BG_BYTES_PER_WARP;
+  // q/k LayerNorm parameters of the fused QKV epilogue: [q w | q b | k w | k b] x 64 fp32
+  static constexpr int QK_OFFSET = BG_OFFSET + kNumEpiWarps * BG_BYTES_PER_WARP;
+  static constexpr int BAR_OFFSET = QK_OFFSET + 4 * 64 * 4;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024: manual alignment slack
 };
 
@@ -78,7 +89,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 //         into both CTAs, so a CTA pulls 32 KB instead of 48 KB through L2 per k block. Reason (ncu, qkv-shaped GEMM):
 //         the MMA warp spent 58 % of its time waiting on the TMA full barriers — with 192 KB of smem the ring holds
 //         just enough bytes in flight for 96 B/clk/SM at the loaded L2 latency; at 64 B/clk/SM it does.
-template <int BLOCK_N, int STAGES, bool TF32, int CL>
+template <int BLOCK_N, int STAGES, bool TF32, int CL, bool QK>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<BLOCK_N, STAGES>;
@@ -130,6 +141,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
+  if (QK && (p.qk_mode & 1) && threadIdx.x < 256)
+    reinterpret_cast<float*>(smem + S::QK_OFFSET)[threadIdx.x] = __ldg(p.qk_norm + threadIdx.x);
   tc_fence_before();
   if (CL == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything remote touches them
   else __syncthreads();
@@ -226,6 +239,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       __syncwarp();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (QK) {
+        // ===== fused QKV epilogue (QK instantiations only: the plain kernels keep their register budget): bias -> bf16 -> [LayerNorm(64)] -> [RoPE-2D] -> bf16, one head (64 columns) at a time;
+        // the thread owns its row, so the head's statistics and rotation pairs are all in its own registers. Same
+        // arithmetic as qknorm_rope_kernel (qk_math.cuh): the result is bit-identical to GEMM + stand-alone pass, without
+        // the 822 MB read-modify-write of the q and k thirds.
+        int pos_y = 0, pos_x = 0;
+        if (p.qk_mode & 2) qk_row_position(m_in, p.tokens_per_frame, p.n_special, p.patch_w, pos_y, pos_x);
+        const float* qk_s = reinterpret_cast<const float*>(smem + S::QK_OFFSET);
+#pragma unroll 1
+        for (int hd = 0; hd < COLS_PER_WARP / 64; ++hd) {
+          const int col_in_tile = half * COLS_PER_WARP + hd * 64;
+          const int n0 = n_blk * BLOCK_N + col_in_tile;
+          if (n0 >= p.N) break;  // warp-uniform
+          uint32_t r[64];
+          const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N + col_in_tile;
+          tmem_ld_x32(taddr, r);
+          tmem_ld_x32(taddr + 32, r + 32);
+          tmem_ld_wait();
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_s + hd * 64 + j);
+            v[j] = qk_round_bf16(__fadd_rn(__uint_as_float(r[j]), b.x));
+            v[j + 1] = qk_round_bf16(__fadd_rn(__uint_as_float(r[j + 1]), b.y));
+            v[j + 2] = qk_round_bf16(__fadd_rn(__uint_as_float(r[j + 2]), b.z));
+            v[j + 3] = qk_round_bf16(__fadd_rn(__uint_as_float(r[j + 3]), b.w));
+          }
+          if (n0 < p.qk_cols) {
+            const float* nw = (p.qk_mode & 1) ? qk_s + (n0 >= (p.qk_cols >> 1) ? 128 : 0) : nullptr;
+            qk_head_inplace(v, nw, nw + 64, p.qk_eps, (p.qk_mode & 2) ? p.cs_table : nullptr, pos_y, pos_x);
+          }
+          if (row_ok) {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + size_t(m) * p.ldo + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
         const int col_in_tile = half * COLS_PER_WARP + c * 32;
@@ -354,11 +407,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BLOCK_N, int STAGES, bool TF32, int CL>
+template <int BLOCK_N, int STAGES, bool TF32, int CL, bool QK = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
                        cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N, STAGES>;
-  auto kern = gemm_kernel<BLOCK_N, STAGES, TF32, CL>;
+  auto kern = gemm_kernel<BLOCK_N, STAGES, TF32, CL, QK>;
   static DeviceOnce configured;   // one per template instantiation; the attribute is per device
   const int dev = current_device();
   if (configured.first_call_on(dev)) {
@@ -394,23 +447,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 using namespace pi3b;
 
-// See include/pi3b200.h for the contract.
-extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda, const void* W, int64_t ldw, int M,
-                         int N, int K, const float* bias, const float* gamma, const float* resid, int64_t ld_resid,
-                         void* out, int64_t ldo, int out_f32, int act, int grp_in, int grp_out, int grp_off) {
-  PI3B_REQUIRE(A && W && out, "pi3b_gemm: null pointer");
-  PI3B_REQUIRE(M > 0 && N > 0 && K > 0, "pi3b_gemm: bad shape M=%d N=%d K=%d", M, N, K);
-  PI3B_REQUIRE(in_dtype == 0 || in_dtype == 1, "pi3b_gemm: in_dtype must be 0 (bf16) or 1 (fp32->tf32)");
-  PI3B_REQUIRE(act >= 0 && act <= 2, "pi3b_gemm: act must be 0/1/2");
-  PI3B_REQUIRE(grp_in == 0 || (grp_in > 0 && grp_out >= grp_in + grp_off && grp_off >= 0), "pi3b_gemm: bad row remap");
+// shared by pi3b_gemm and pi3b_gemm_qkv: tile choice, tensor maps, launch
+static int gemm_dispatch(void* stream, int in_dtype, const void* A, int64_t lda, const void* W, int64_t ldw, GemmParams p) {
+  const int M = p.M, N = p.N, K = p.K;
   const int esz = in_dtype == 0 ? 2 : 4;
-  PI3B_REQUIRE((lda * esz) % 16 == 0 && (ldw * esz) % 16 == 0, "pi3b_gemm: lda/ldw must give 16-byte row pitch");
-  PI3B_REQUIRE(lda >= K && ldw >= K, "pi3b_gemm: lda/ldw < K");
-  PI3B_REQUIRE(ldo >= N && (!resid || ld_resid >= N), "pi3b_gemm: ldo/ld_resid < N");
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  const int vec_ok = (ldo % (out_f32 ? 4 : 8) == 0) && al16(out) && (!resid || (ld_resid % 4 == 0 && al16(resid))) &&
-                     (!bias || al16(bias)) && (!gamma || al16(gamma));
-
   const int num_sms = num_sms_of(current_device());
   const int block_k = 128 / esz;
   // Use the wide tile when it still fills the machine; otherwise the narrow tile for more CTAs.
@@ -425,14 +465,12 @@ extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda,
   if (rc) return rc;
   rc = make_tmap_2d(&tmB, W, in_dtype, (uint64_t)N, (uint64_t)K, (uint64_t)ldw * esz, (wide && !cluster) ? 256 : 128, block_k);
   if (rc) return rc;
-
-  GemmParams p;
-  p.M = M; p.N = N; p.K = K;
-  p.bias = bias; p.gamma = gamma; p.resid = resid;
-  p.out = out; p.ldo = (int)ldo; p.ld_resid = (int)ld_resid;
-  p.out_f32 = out_f32; p.act = act; p.vec_ok = vec_ok;
-  p.grp_in = grp_in; p.grp_out = grp_out; p.grp_off = grp_off;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p.qk_mode != 0) {   // fused QKV epilogue (bf16 operands only)
+    if (cluster) return launch_gemm<256, 4, false, 2, true>(tmA, tmB, p, num_sms, st);
+    return wide ? launch_gemm<256, 4, false, 1, true>(tmA, tmB, p, num_sms, st)
+                : launch_gemm<128, 6, false, 1, true>(tmA, tmB, p, num_sms, st);
+  }
   if (in_dtype == 0) {
     if (cluster) return launch_gemm<256, 4, false, 2>(tmA, tmB, p, num_sms, st);
     return wide ? launch_gemm<256, 4, false, 1>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, false, 1>(tmA, tmB, p, num_sms, st);
@@ -440,4 +478,62 @@ extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda,
     if (cluster) return launch_gemm<256, 4, true, 2>(tmA, tmB, p, num_sms, st);
     return wide ? launch_gemm<256, 4, true, 1>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, true, 1>(tmA, tmB, p, num_sms, st);
   }
+}
+
+static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+// See include/pi3b200.h for the contract.
+extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda, const void* W, int64_t ldw, int M,
+                         int N, int K, const float* bias, const float* gamma, const float* resid, int64_t ld_resid,
+                         void* out, int64_t ldo, int out_f32, int act, int grp_in, int grp_out, int grp_off) {
+  PI3B_REQUIRE(A && W && out, "pi3b_gemm: null pointer");
+  PI3B_REQUIRE(M > 0 && N > 0 && K > 0, "pi3b_gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  PI3B_REQUIRE(in_dtype == 0 || in_dtype == 1, "pi3b_gemm: in_dtype must be 0 (bf16) or 1 (fp32->tf32)");
+  PI3B_REQUIRE(act >= 0 && act <= 2, "pi3b_gemm: act must be 0/1/2");
+  PI3B_REQUIRE(grp_in == 0 || (grp_in > 0 && grp_out >= grp_in + grp_off && grp_off >= 0), "pi3b_gemm: bad row remap");
+  const int esz = in_dtype == 0 ? 2 : 4;
+  PI3B_REQUIRE((lda * esz) % 16 == 0 && (ldw * esz) % 16 == 0, "pi3b_gemm: lda/ldw must give 16-byte row pitch");
+  PI3B_REQUIRE(lda >= K && ldw >= K, "pi3b_gemm: lda/ldw < K");
+  PI3B_REQUIRE(ldo >= N && (!resid || ld_resid >= N), "pi3b_gemm: ldo/ld_resid < N");
+  const int vec_ok = (ldo % (out_f32 ? 4 : 8) == 0) && al16(out) && (!resid || (ld_resid % 4 == 0 && al16(resid))) &&
+                     (!bias || al16(bias)) && (!gamma || al16(gamma));
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.gamma = gamma; p.resid = resid;
+  p.out = out; p.ldo = (int)ldo; p.ld_resid = (int)ld_resid;
+  p.out_f32 = out_f32; p.act = act; p.vec_ok = vec_ok;
+  p.grp_in = grp_in; p.grp_out = grp_out; p.grp_off = grp_off;
+  return gemm_dispatch(stream, in_dtype, A, lda, W, ldw, p);
+}
+
+extern "C" int pi3b_gemm_qkv(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int num_heads,
+                             int K, const float* bias, void* out, int64_t ldo, const float* qk_norm, float eps,
+                             const float* cs_table, int table_rows, int tokens_per_frame, int n_special, int patch_w) {
+  PI3B_REQUIRE(A && W && out, "pi3b_gemm_qkv: null pointer");
+  PI3B_REQUIRE(M > 0 && num_heads > 0 && K > 0, "pi3b_gemm_qkv: bad shape");
+  PI3B_REQUIRE(qk_norm || cs_table, "pi3b_gemm_qkv: neither q/k norm nor RoPE requested (use pi3b_gemm)");
+  const int N = 3 * 64 * num_heads;
+  PI3B_REQUIRE((lda * 2) % 16 == 0 && (ldw * 2) % 16 == 0 && lda >= K && ldw >= K, "pi3b_gemm_qkv: bad lda/ldw");
+  PI3B_REQUIRE(ldo >= N && ldo % 8 == 0 && al16(out) && (!bias || al16(bias)) && (!qk_norm || al16(qk_norm)),
+               "pi3b_gemm_qkv: out / bias / qk_norm must be 16-byte aligned, ldo a multiple of 8");
+  if (cs_table) {
+    PI3B_REQUIRE(al16(cs_table) && tokens_per_frame > n_special && n_special >= 0 && patch_w > 0,
+                 "pi3b_gemm_qkv: bad RoPE geometry");
+    const int ph = (tokens_per_frame - n_special + patch_w - 1) / patch_w;
+    PI3B_REQUIRE(table_rows > (ph > patch_w ? ph : patch_w), "pi3b_gemm_qkv: cos/sin table too short");
+  }
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias;
+  p.out = out; p.ldo = (int)ldo;
+  p.vec_ok = 1;
+  p.qk_mode = (qk_norm ? 1 : 0) | (cs_table ? 2 : 0);
+  p.qk_cols = 2 * 64 * num_heads;
+  p.qk_norm = qk_norm;
+  p.cs_table = reinterpret_cast<const float2*>(cs_table);
+  p.qk_eps = eps;
+  p.tokens_per_frame = tokens_per_frame > 0 ? tokens_per_frame : 1;
+  p.n_special = n_special;
+  p.patch_w = patch_w > 0 ? patch_w : 1;
+  return gemm_dispatch(stream, 0, A, lda, W, ldw, p);
 }

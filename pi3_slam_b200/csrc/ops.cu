@@ -2,6 +2,7 @@
 // broadcast, head unpatchify (+exp, xy*z, pose transform), token mean-pool, 9D->SO(3) pose, validity mask.
 // All are coalesced / 16-byte vectorised streaming kernels; none reshapes its work into a GEMM.
 #include "host_common.h"
+#include "qk_math.cuh"
 
 #include <cuda_bf16.h>
 #include <math.h>
@@ -131,26 +132,20 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(__nv_bfloat16* __restr
     const bool ok = row < M;  // uniform inside an 8-lane group; shuffles below stay convergent for the full warp
     float x[8] = {bf_lo(raw[r].x), bf_hi(raw[r].x), bf_lo(raw[r].y), bf_hi(raw[r].y),
                   bf_lo(raw[r].z), bf_hi(raw[r].z), bf_lo(raw[r].w), bf_hi(raw[r].w)};
+    // arithmetic order shared with the fused QKV-GEMM epilogue (qk_math.cuh): bit-identical results
     if (nw) {
-      float s = 0.f;
+      float s = qk_sum8(x);
+      s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));
+      s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 2));
+      s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 4));
+      const float mean = qk_mean(s);
+      float q = qk_sq8(x, mean);
+      q = __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 1));
+      q = __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 2));
+      q = __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 4));
+      const float rstd = qk_rstd(q, eps);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += x[i];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      const float mean = s * (1.0f / 64.0f);
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) q += (x[i] - mean) * (x[i] - mean);
-      q += __shfl_xor_sync(0xffffffffu, q, 1);
-      q += __shfl_xor_sync(0xffffffffu, q, 2);
-      q += __shfl_xor_sync(0xffffffffu, q, 4);
-      const float rstd = rsqrtf(q * (1.0f / 64.0f) + eps);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float y = (x[i] - mean) * rstd * w8[i] + b8[i];
-        x[i] = __bfloat162float(__float2bfloat16(y));  // reference casts the normed q/k to bf16 before RoPE
-      }
+      for (int i = 0; i < 8; ++i) x[i] = qk_norm1(x[i], mean, rstd, w8[i], b8[i]);
     }
     if (do_rope) {
       const int t = int(uint32_t(row) % uint32_t(tokens_per_frame));
@@ -168,8 +163,9 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(__nv_bfloat16* __restr
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 c = __ldg(cs + i);  // (cos, sin) of two consecutive frequencies
-          x[2 * i] = is_v ? (x[2 * i] * c.x + partner[2 * i] * c.y) : (x[2 * i] * c.x - partner[2 * i] * c.y);
-          x[2 * i + 1] = is_v ? (x[2 * i + 1] * c.z + partner[2 * i + 1] * c.w) : (x[2 * i + 1] * c.z - partner[2 * i + 1] * c.w);
+          x[2 * i] = is_v ? qk_rope_second(partner[2 * i], x[2 * i], c.x, c.y) : qk_rope_first(x[2 * i], partner[2 * i], c.x, c.y);
+          x[2 * i + 1] = is_v ? qk_rope_second(partner[2 * i + 1], x[2 * i + 1], c.z, c.w)
+                              : qk_rope_first(x[2 * i + 1], partner[2 * i + 1], c.z, c.w);
         }
       }
     }

@@ -92,6 +92,34 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
     return out
 
 
+def gemm_qkv(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor], num_heads: int,
+             qk_norm: Optional[torch.Tensor], eps: float, cs_table: Optional[torch.Tensor], tokens_per_frame: int,
+             n_special: int, patch_w: int) -> torch.Tensor:
+    """QKV projection with q/k LayerNorm(64) and RoPE-2D fused into the GEMM epilogue (bit-identical to `gemm` followed by
+    `qknorm_rope`). a [M,K], w [3*64*heads, K] bf16; out [M, 3*64*heads] bf16; qk_norm fp32 [4,64] (q weight, q bias,
+    k weight, k bias) or None; cs_table fp32 [max_pos+1, 16, 2] or None."""
+    lib = _lib.load()
+    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w"); _req(out, torch.bfloat16, "out")
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    M, K = a.shape
+    assert w.shape == (3 * 64 * num_heads, K) and out.shape == (M, 3 * 64 * num_heads)
+    rows = 0
+    if qk_norm is not None:
+        _req(qk_norm, torch.float32, "qk_norm")
+        assert qk_norm.is_contiguous() and qk_norm.numel() == 256
+    if cs_table is not None:
+        _req(cs_table, torch.float32, "cs_table")
+        assert cs_table.is_contiguous() and cs_table.shape[1:] == (16, 2)
+        rows = cs_table.shape[0]
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    rc = lib.pi3b_gemm_qkv(_stream(), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, num_heads, K, _ptr(bias),
+                           out.data_ptr(), out.stride(0), _ptr(qk_norm), eps, _ptr(cs_table), rows, tokens_per_frame,
+                           n_special, patch_w)
+    _lib.check(rc, "pi3b_gemm_qkv")
+    return out
+
+
 def attention_qkv(qkv: torch.Tensor, out: torch.Tensor, num_seqs: int, seq_len: int, num_heads: int = 16,
                   scale: float = 0.125) -> torch.Tensor:
     """softmax(q k^T * scale) v per (sequence, head), head_dim 64.

@@ -78,6 +78,9 @@ class Pi3(nn.Module):
         # NVLink, then merge through the log-sum-exp (exposed all-gather ~0, result within bf16 tolerance of the
         # single-GPU forward); False = blocking all-gather, one attention over all keys (bit-identical to one GPU)
         self.sp_overlap: bool = True
+        # q/k LayerNorm + RoPE fused into the QKV GEMM epilogue (bit-identical to the separate pi3b_qknorm_rope pass, which
+        # PI3B_FUSE_QK=0 brings back for A/B runs)
+        self.fuse_qk_epilogue: bool = os.environ.get("PI3B_FUSE_QK", "1") != "0"
         # when set to a list, (local_done, gather_done) CUDA events of every sequence-parallel layer are appended:
         # their distance is the all-gather time the local attention did not hide
         self.sp_events: Optional[list] = None
@@ -163,6 +166,8 @@ class Pi3(nn.Module):
                 "qn": (f32(prefix + ".attn.q_norm.weight"), f32(prefix + ".attn.q_norm.bias")) if qkn else None,
                 "kn": (f32(prefix + ".attn.k_norm.weight"), f32(prefix + ".attn.k_norm.bias")) if qkn else None,
             }
+            # fused QKV epilogue: [q weight | q bias | k weight | k bias] x 64
+            b["qkn"] = torch.cat([b["qn"][0], b["qn"][1], b["kn"][0], b["kn"][1]]).contiguous() if qkn else None
             return b
 
         wp = torch.zeros(D, K_PATCH_PAD, device=device, dtype=torch.bfloat16)
@@ -334,9 +339,13 @@ class Pi3(nn.Module):
         every rank of the group, all-gathered over NCCL."""
         h, qkv, att, mlp = bufs["h"], bufs["qkv"], bufs["att"], bufs["mlp"]
         ops.layernorm(x, b["n1"][0], b["n1"][1], 1e-6, h)
-        ops.gemm(h, b["qkv_w"], qkv, bias=b["qkv_b"])
-        if rope or b["qn"] is not None:
-            ops.qknorm_rope(qkv, HEADS, T, N_SPECIAL, pw, cs if rope else None, b["qn"], b["kn"], 1e-5)
+        if (rope or b["qn"] is not None) and self.fuse_qk_epilogue:
+            # q/k LayerNorm(64) + RoPE-2D inside the QKV GEMM's epilogue (one launch, no extra pass over q and k)
+            ops.gemm_qkv(h, b["qkv_w"], qkv, b["qkv_b"], HEADS, b["qkn"], 1e-5, cs if rope else None, T, N_SPECIAL, pw)
+        else:
+            ops.gemm(h, b["qkv_w"], qkv, bias=b["qkv_b"])
+            if rope or b["qn"] is not None:
+                ops.qknorm_rope(qkv, HEADS, T, N_SPECIAL, pw, cs if rope else None, b["qn"], b["kn"], 1e-5)
         if sp is not None:
             self._sp_global_attention(qkv, att, bufs, sp, seq_len)
         elif self.global_attn_events is not None and seq_len != T:

@@ -66,3 +66,36 @@ def test_gemm_matches_torch(M, N, K, dt, out_f32, has_bias, has_gamma, has_resid
     assert err.item() < tol, f"rel err {err.item():.3e}"
     maxabs = (out.float() - ref).abs().max().item()
     assert maxabs < 0.05 * max(1.0, ref.abs().max().item())
+
+
+# M: narrow-tile path (< 148 wide tiles), wide single-CTA path (PI3B_GEMM_CLUSTER=0 in the subprocess case below) and the
+# default wide 2-CTA-cluster path; ragged M tails; (norm, rope) combinations used by the model: decoder blocks (both),
+# head decoders (rope only).
+@pytest.mark.parametrize("M,T,pw", [(643 * 3, 643, 29), (1004 * 20, 1004, 37), (261 * 5 + 7, 261, 16)])
+@pytest.mark.parametrize("norm,rope", [(True, True), (False, True), (True, False)])
+def test_fused_qkv_epilogue_is_bit_identical_to_gemm_plus_qknorm_rope(M, T, pw, norm, rope):
+    """pi3b_gemm_qkv == pi3b_gemm followed by pi3b_qknorm_rope, bit for bit (shared arithmetic, csrc/qk_math.cuh)."""
+    from pi3_slam_b200 import ops
+
+    H, K = 16, 1024
+    torch.manual_seed(M + T)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(3 * 64 * H, K, device="cuda") * 0.03).bfloat16()
+    bias = torch.randn(3 * 64 * H, device="cuda") * 0.1
+    qn = (torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda") * 0.1)
+    kn = (torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda") * 0.1)
+    qkn = torch.cat([qn[0], qn[1], kn[0], kn[1]]).contiguous()
+    max_pos = max(pw, (T - 5 + pw - 1) // pw)
+    inv_freq = 1.0 / (100.0 ** (torch.arange(0, 32, 2).float() / 32))
+    ang = torch.einsum("i,j->ij", torch.arange(max_pos + 1, dtype=torch.float32), inv_freq)
+    cs = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous().cuda()
+
+    want = torch.empty(M, 3 * 64 * H, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, want, bias=bias)
+    ops.qknorm_rope(want, H, T, 5, pw, cs if rope else None, qn if norm else None, kn if norm else None, 1e-5)
+    got = torch.full_like(want, float("nan"))
+    ops.gemm_qkv(a, w, got, bias, H, qkn if norm else None, 1e-5, cs if rope else None, T, 5, pw)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all()
+    neq = (got.view(torch.int16) != want.view(torch.int16)).sum().item()
+    assert neq == 0, f"{neq} of {got.numel()} elements differ, max |d| {(got.float() - want.float()).abs().max().item():.3e}"

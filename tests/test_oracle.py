@@ -100,3 +100,28 @@ def test_view_graph_matches():
     from oracle.chunk_oracle import create_view_graph_matches
     assert create_view_graph_matches(100, 20)[0] == (80, 0) and create_view_graph_matches(100, 20)[-1] == (99, 19)
     assert create_view_graph_matches(8, 2) == [(6, 0), (7, 1)]
+
+
+def test_rope2d_restatement_matches_the_reference_native_kernel_source():
+    """oracle.rope2d against the reference's own curope extension (pi3/models/curope/curope.cpp rope_2d, CPU path), built
+    from the reference sources by oracle/build_ref_curope.py into oracle/_ref/ (skipped where that library is absent)."""
+    import importlib.util
+    import os
+
+    import pytest
+    import torch
+    from oracle.pi3_oracle import rope2d
+
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_curope.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/ref_curope.so not built")
+    spec = importlib.util.spec_from_file_location("ref_curope", so)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    g = torch.Generator().manual_seed(3)
+    tok = torch.randn(2, 50, 4, 64, generator=g)
+    pos = torch.randint(0, 40, (2, 50, 2), generator=g)
+    want = rope2d(tok.transpose(1, 2), pos).transpose(1, 2)
+    got = tok.clone()
+    ref.rope_2d(got, pos, 100.0, 1.0)
+    assert (got - want).abs().max().item() < 5e-6

@@ -135,3 +135,20 @@ def test_repeated_calls_are_deterministic_and_shape_switching_works(model_and_sd
         assert torch.equal(r1[k], r2[k]), k
     with pytest.raises(ValueError):
         model(torch.rand(1, 2, 3, 40, 56, device="cuda"))      # H not a multiple of 14
+
+
+def test_fused_qk_epilogue_forward_is_bit_identical_to_separate_pass(model_and_sd):
+    """Pi3.fuse_qk_epilogue (q/k LayerNorm + RoPE inside the QKV GEMM) must not change a single output bit."""
+    from pi3_slam_b200.synthetic import make_frames
+
+    model, _ = model_and_sd
+    imgs = make_frames(3, 56, 70)[None].cuda()
+    assert model.fuse_qk_epilogue
+    fused = {k: v.clone() for k, v in model(imgs).items()}
+    model.fuse_qk_epilogue = False
+    try:
+        plain = model(imgs)
+    finally:
+        model.fuse_qk_epilogue = True
+    for k in fused:
+        assert torch.equal(fused[k], plain[k]), k
