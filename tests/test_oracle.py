@@ -124,4 +124,4 @@ def test_rope2d_restatement_matches_the_reference_native_kernel_source():
     want = rope2d(tok.transpose(1, 2), pos).transpose(1, 2)
     got = tok.clone()
     ref.rope_2d(got, pos, 100.0, 1.0)
-    assert (got - want).abs().max().item() < 5e-6
+    assert (got - want).abs().max().item() < 2e-5     # fp32 cosf/sinf/powf at angles up to 40 rad
