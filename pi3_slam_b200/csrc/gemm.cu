@@ -246,7 +246,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // the 822 MB read-modify-write of the q and k thirds.
         int pos_y = 0, pos_x = 0;
         if (p.qk_mode & 2) qk_row_position(m_in, p.tokens_per_frame, p.n_special, p.patch_w, pos_y, pos_x);
-        const float* qk_s = reinterpret_cast<const float*>(smem + S::QK_OFFSET);
+        const uint32_t qk_saddr = smem_u32(smem + S::QK_OFFSET);
+        const uint32_t bias_saddr = smem_u32(bias_s);
 #pragma unroll 1
         for (int hd = 0; hd < COLS_PER_WARP / 64; ++hd) {
           const int col_in_tile = half * COLS_PER_WARP + hd * 64;
@@ -260,15 +261,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           float v[64];
 #pragma unroll
           for (int j = 0; j < 64; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias_s + hd * 64 + j);
-            v[j] = qk_round_bf16(__fadd_rn(__uint_as_float(r[j]), b.x));
-            v[j + 1] = qk_round_bf16(__fadd_rn(__uint_as_float(r[j + 1]), b.y));
-            v[j + 2] = qk_round_bf16(__fadd_rn(__uint_as_float(r[j + 2]), b.z));
-            v[j + 3] = qk_round_bf16(__fadd_rn(__uint_as_float(r[j + 3]), b.w));
+            const float4 b = qk_lds128(bias_saddr + (hd * 64 + j) * 4);
+            v[j] = __fadd_rn(__uint_as_float(r[j]), b.x);
+            v[j + 1] = __fadd_rn(__uint_as_float(r[j + 1]), b.y);
+            v[j + 2] = __fadd_rn(__uint_as_float(r[j + 2]), b.z);
+            v[j + 3] = __fadd_rn(__uint_as_float(r[j + 3]), b.w);
+            qk_round_bf16_x2(v[j], v[j + 1]);     // what the plain epilogue would have stored: bf16(acc + bias)
+            qk_round_bf16_x2(v[j + 2], v[j + 3]);
           }
           if (n0 < p.qk_cols) {
-            const float* nw = (p.qk_mode & 1) ? qk_s + (n0 >= (p.qk_cols >> 1) ? 128 : 0) : nullptr;
-            qk_head_inplace(v, nw, nw + 64, p.qk_eps, (p.qk_mode & 2) ? p.cs_table : nullptr, pos_y, pos_x);
+            const uint32_t norm_saddr = (p.qk_mode & 1) ? qk_saddr + (n0 >= (p.qk_cols >> 1) ? 512u : 0u) : 0u;
+            qk_head_inplace(v, norm_saddr, p.qk_eps, (p.qk_mode & 2) ? p.cs_table : nullptr, pos_y, pos_x);
           }
           if (row_ok) {
             uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + size_t(m) * p.ldo + n0);

@@ -44,12 +44,28 @@ __device__ __forceinline__ float qk_norm1(float x, float mean, float rstd, float
 __device__ __forceinline__ float qk_rope_first(float a, float b, float c, float s) { return __fmaf_rn(a, c, -__fmul_rn(b, s)); }
 __device__ __forceinline__ float qk_rope_second(float a, float b, float c, float s) { return __fmaf_rn(b, c, __fmul_rn(a, s)); }
 
-// One whole head held by one thread: v[64] (fp32 values that are exact bf16 numbers) -> LayerNorm (if nw != nullptr;
-// nw / nb point to 64 floats, 16-byte aligned, shared or global) -> RoPE with positions (pos_y, pos_x) (if cs != nullptr;
+// 16-byte load from shared memory by 32-bit shared address (pointers derived from the manually aligned dynamic smem base
+// are generic to the compiler, which would emit slower generic loads)
+__device__ __forceinline__ float4 qk_lds128(uint32_t saddr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+  return r;
+}
+// two values rounded to bf16 at once (one F2FP pack + two ALU unpacks instead of two XU-pipe F2F conversions + shifts);
+// same round-to-nearest-even as qk_round_bf16
+__device__ __forceinline__ void qk_round_bf16_x2(float& a, float& b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const uint32_t u = *reinterpret_cast<uint32_t*>(&h);
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xffff0000u);
+}
+
+// One whole head held by one thread: v[64] (fp32 values that are exact bf16 numbers) -> LayerNorm (if norm_saddr != 0: the
+// shared-memory address of 64 weights followed by 64 biases) -> RoPE with positions (pos_y, pos_x) (if cs != nullptr;
 // cs = fp32 [pos][16] (cos, sin)). Results are left in v (unrounded after RoPE: the caller packs to bf16).
-__device__ __forceinline__ void qk_head_inplace(float* v, const float* nw, const float* nb, float eps, const float2* cs,
-                                                int pos_y, int pos_x) {
-  if (nw != nullptr) {
+__device__ __forceinline__ void qk_head_inplace(float* v, uint32_t norm_saddr, float eps, const float2* cs, int pos_y,
+                                                int pos_x) {
+  if (norm_saddr != 0) {
     float part[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) part[g] = qk_sum8(v + 8 * g);
@@ -59,12 +75,15 @@ __device__ __forceinline__ void qk_head_inplace(float* v, const float* nw, const
     const float rstd = qk_rstd(qk_tree8(part), eps);
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
-      const float4 w4 = *reinterpret_cast<const float4*>(nw + i);
-      const float4 b4 = *reinterpret_cast<const float4*>(nb + i);
-      v[i] = qk_norm1(v[i], mean, rstd, w4.x, b4.x);
-      v[i + 1] = qk_norm1(v[i + 1], mean, rstd, w4.y, b4.y);
-      v[i + 2] = qk_norm1(v[i + 2], mean, rstd, w4.z, b4.z);
-      v[i + 3] = qk_norm1(v[i + 3], mean, rstd, w4.w, b4.w);
+      const float4 w4 = qk_lds128(norm_saddr + i * 4);
+      const float4 b4 = qk_lds128(norm_saddr + 256 + i * 4);
+      float y0 = __fmaf_rn(__fmul_rn(__fsub_rn(v[i], mean), rstd), w4.x, b4.x);
+      float y1 = __fmaf_rn(__fmul_rn(__fsub_rn(v[i + 1], mean), rstd), w4.y, b4.y);
+      float y2 = __fmaf_rn(__fmul_rn(__fsub_rn(v[i + 2], mean), rstd), w4.z, b4.z);
+      float y3 = __fmaf_rn(__fmul_rn(__fsub_rn(v[i + 3], mean), rstd), w4.w, b4.w);
+      qk_round_bf16_x2(y0, y1);
+      qk_round_bf16_x2(y2, y3);
+      v[i] = y0; v[i + 1] = y1; v[i + 2] = y2; v[i + 3] = y3;
     }
   }
   if (cs != nullptr) {
