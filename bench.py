@@ -432,7 +432,8 @@ def main():
     if world > 1:
         # keep stdout to the single JSON line: NCCL writes its version banner / debug output to stdout by default
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        from pi3_slam_b200.host.datasets import nccl_high_priority_options
+        dist.init_process_group("nccl", device_id=dev, pg_options=nccl_high_priority_options())
 
     sd = make_state_dict(0)
     model = Pi3()

@@ -46,10 +46,10 @@ constexpr int kBlockM = 128;
 constexpr int kNumEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kNumEpiWarps * 32;
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool TWOSM = false>
 struct GemmSmem {
   static constexpr int A_BYTES = kBlockM * 128;
-  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int B_BYTES = (TWOSM ? BLOCK_N / 2 : BLOCK_N) * 128;   // 2-SM: each CTA of the pair holds half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // per-epilogue-warp transpose staging: 32 rows x 16 fp32 (+4 pad so rows stay 16-byte aligned and the
   // 128-bit accesses of 8 consecutive rows fall into distinct bank groups)
@@ -89,10 +89,17 @@ __device__ __forceinline__ float gelu_erf(float x) {
 //         into both CTAs, so a CTA pulls 32 KB instead of 48 KB through L2 per k block. Reason (ncu, qkv-shaped GEMM):
 //         the MMA warp spent 58 % of its time waiting on the TMA full barriers — with 192 KB of smem the ring holds
 //         just enough bytes in flight for 96 B/clk/SM at the loaded L2 latency; at 64 B/clk/SM it does.
-template <int BLOCK_N, int STAGES, bool TF32, int CL, bool QK>
+// TWOSM (CL = 2 only): the two CTAs of the cluster form a CTA PAIR and execute one tcgen05.mma.cta_group::2 of M = 256:
+//         a 256 x BLOCK_N output tile per pair, each CTA loading its 128 rows of A and HALF of the B tile (nothing is
+//         duplicated: 32 KB per CTA and k block through L2 and into shared memory instead of 48 KB, and the tensor core
+//         reads half of B from its own shared memory, the other half from the peer's). The even CTA issues all MMAs and
+//         owns the full and accumulator-empty barriers; see ptx.cuh. This is the configuration cuBLAS picks for these
+//         shapes on B200 (nvjet 256x256_64x4 2cta, profiles/r02_gemm_full_metrics.txt).
+template <int BLOCK_N, int STAGES, bool TF32, int CL, bool QK, bool TWOSM = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using S = GemmSmem<BLOCK_N, STAGES>;
+  static_assert(!TWOSM || (CL == 2 && !TF32), "the CTA-pair kernel is the bf16 2-CTA-cluster variant");
+  using S = GemmSmem<BLOCK_N, STAGES, TWOSM>;
   constexpr int ELEM = TF32 ? 4 : 2;
   constexpr int BLOCK_K = 128 / ELEM;  // elements per 128-byte smem row
   constexpr int UMMA_K = 32 / ELEM;    // 16 (bf16) / 8 (tf32): 32 bytes of K per instruction
@@ -129,17 +136,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);  // the slot is reused only when every CTA that receives multicast data has consumed it
+      // the slot is reused only when every CTA that receives multicast data has consumed it (CTA pair: one multicast
+      // commit of the pair's MMAs arrives once on each CTA)
+      mbar_init(&empty_bar[i], TWOSM ? 1 : CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kNumEpiWarps);
+      // CTA pair: the epilogue warps of BOTH CTAs hand the accumulator stage back to the leader's barrier
+      mbar_init(&tmem_empty[i], TWOSM ? 2 * kNumEpiWarps : kNumEpiWarps);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (TWOSM) {
+      tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   if (QK && (p.qk_mode & 1) && threadIdx.x < 256)
     reinterpret_cast<float*>(smem + S::QK_OFFSET)[threadIdx.x] = __ldg(p.qk_norm + threadIdx.x);
@@ -160,6 +175,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
+          if (TWOSM) {
+            // CTA pair: both CTAs' bytes are credited to the leader's barrier, which therefore expects twice a stage
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+            tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * kBlockM, kEvictNormal);
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2), kEvictLast);
+          } else {
           mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           // activations stream through once; the (small) weight panel is reused by every m block
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * kBlockM, kEvictNormal);
@@ -168,14 +189,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                               n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2), uint16_t(3), kEvictLast);
           else
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, kEvictLast);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (!TWOSM || cta_rank == 0)) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit =====
-    constexpr uint32_t idesc = make_idesc(TF32 ? 2u : 1u, kBlockM, BLOCK_N, 0, 0);
+    constexpr uint32_t idesc = make_idesc(TF32 ? 2u : 1u, TWOSM ? 2 * kBlockM : kBlockM, BLOCK_N, 0, 0);
     const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
     const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem + S::A_BYTES), 16, 1024);
     int stage = 0;
@@ -193,15 +215,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            if (TF32)
+            if (TWOSM)
+              umma_f16_ss_2sm(d_tmem, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (kb | k) != 0);
+            else if (TF32)
               umma_tf32_ss(d_tmem, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (kb | k) != 0);
             else
               umma_f16_ss(d_tmem, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (kb | k) != 0);
           }
-          // frees the smem slot once these MMAs have read it (in both CTAs of a cluster: the peer multicasts into it)
-          if (CL == 2) umma_commit_mcast(&empty_bar[stage], uint16_t(3));
+          // frees the smem slot once these MMAs have read it (in both CTAs of a cluster: the peer multicasts into it /
+          // the pair's MMA reads both CTAs' slots)
+          if (TWOSM) umma_commit_2sm(&empty_bar[stage], uint16_t(3));
+          else if (CL == 2) umma_commit_mcast(&empty_bar[stage], uint16_t(3));
           else umma_commit(&empty_bar[stage]);
-          if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          if (kb == num_k - 1) {  // accumulator complete -> epilogue (of both CTAs of a pair)
+            if (TWOSM) umma_commit_2sm(&tmem_full[acc], uint16_t(3));
+            else umma_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -209,7 +238,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else {
+  } else if (warp >= 2) {
     // ===== epilogue warps: TMEM -> registers -> fused epilogue -> HBM =====
     const int ew = warp - 2;
     const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
@@ -395,7 +424,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (TWOSM) mbar_arrive_cluster(&tmem_empty[acc], 0);   // the leader's MMA warp waits for both CTAs' epilogues
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -406,15 +438,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (TWOSM) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int BLOCK_N, int STAGES, bool TF32, int CL, bool QK = false>
+template <int BLOCK_N, int STAGES, bool TF32, int CL, bool QK = false, bool TWOSM = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
                        cudaStream_t stream) {
-  using S = GemmSmem<BLOCK_N, STAGES>;
-  auto kern = gemm_kernel<BLOCK_N, STAGES, TF32, CL, QK>;
+  using S = GemmSmem<BLOCK_N, STAGES, TWOSM>;
+  auto kern = gemm_kernel<BLOCK_N, STAGES, TF32, CL, QK, TWOSM>;
   static DeviceOnce configured;   // one per template instantiation; the attribute is per device
   const int dev = current_device();
   if (configured.first_call_on(dev)) {
@@ -462,19 +495,25 @@ static int gemm_dispatch(void* stream, int in_dtype, const void* A, int64_t lda,
   // wide tiles run as 2-CTA clusters sharing the B tile through TMA multicast (PI3B_GEMM_CLUSTER=0 disables, for A/B runs)
   static const bool cluster_ok = []() { const char* e = getenv("PI3B_GEMM_CLUSTER"); return !(e && e[0] == '0'); }();
   const bool cluster = wide && cluster_ok && M > 128;
+  // bf16 wide tiles: CTA pairs (cta_group::2, 256 x 256 per pair); PI3B_GEMM_2SM=0 falls back to the multicast clusters
+  static const bool twosm_ok = []() { const char* e = getenv("PI3B_GEMM_2SM"); return !(e && e[0] == '0'); }();
+  const bool twosm = cluster && twosm_ok && in_dtype == 0;
 
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(&tmA, A, in_dtype, (uint64_t)M, (uint64_t)K, (uint64_t)lda * esz, 128, block_k);
   if (rc) return rc;
+  // B box: the whole 256-row tile (single CTA), or the half each CTA of a multicast cluster / CTA pair loads
   rc = make_tmap_2d(&tmB, W, in_dtype, (uint64_t)N, (uint64_t)K, (uint64_t)ldw * esz, (wide && !cluster) ? 256 : 128, block_k);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p.qk_mode != 0) {   // fused QKV epilogue (bf16 operands only)
+    if (twosm) return launch_gemm<256, 6, false, 2, true, true>(tmA, tmB, p, num_sms, st);
     if (cluster) return launch_gemm<256, 4, false, 2, true>(tmA, tmB, p, num_sms, st);
     return wide ? launch_gemm<256, 4, false, 1, true>(tmA, tmB, p, num_sms, st)
                 : launch_gemm<128, 6, false, 1, true>(tmA, tmB, p, num_sms, st);
   }
   if (in_dtype == 0) {
+    if (twosm) return launch_gemm<256, 6, false, 2, false, true>(tmA, tmB, p, num_sms, st);
     if (cluster) return launch_gemm<256, 4, false, 2>(tmA, tmB, p, num_sms, st);
     return wide ? launch_gemm<256, 4, false, 1>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, false, 1>(tmA, tmB, p, num_sms, st);
   } else {

@@ -109,3 +109,18 @@ class ChunkImageDataset(Dataset):
             "end_idx": torch.tensor([end]),
             "chunk_paths": [paths],
         }
+
+
+def nccl_high_priority_options():
+    """ProcessGroupNCCL options that put NCCL's kernels on a HIGH-PRIORITY stream, or None when unavailable. The
+    sequence-parallel K/V all-gather must start while the attention over the local block is running: that kernel
+    occupies every SM (one CTA of 512 threads x 128 registers each) with thousands of CTAs queued behind, and with equal
+    priorities the all-gather kernel is only scheduled once that grid has drained (measured: the whole all-gather
+    exposed, profiles/r02_bench_cfg2_n2_first.json); with a higher priority its few CTAs take the first SMs that free up."""
+    try:
+        import torch.distributed as dist
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        return opts
+    except Exception:
+        return None

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib, ops
 from .host.camera_estimation import camera_parameters_from_samples, sample_for_intrinsics
-from .host.datasets import ChunkImageDataset, plan_waves, split_frames
+from .host.datasets import ChunkImageDataset, nccl_high_priority_options, plan_waves, split_frames
 from .host.image_utils import calculate_target_size, load_images_u8, resize_u8_on_host
 from .host.keypoints import create_keypoint_extractor
 from .pi3 import Pi3
@@ -383,8 +383,11 @@ class OfflineChunkCreator:
         for wave in waves:
             for _, ranks in wave:
                 if len(ranks) > 1 and ranks not in groups:
-                    groups[ranks] = (torch.distributed.group.WORLD if len(ranks) == world
-                                     else torch.distributed.new_group(ranks=list(ranks)))
+                    if len(ranks) == world:
+                        groups[ranks] = torch.distributed.group.WORLD
+                    else:
+                        opts = nccl_high_priority_options() if torch.distributed.get_backend() == "nccl" else None
+                        groups[ranks] = torch.distributed.new_group(ranks=list(ranks), pg_options=opts)
         mine = [(ci, ranks) for wave in waves for ci, ranks in wave if rank in ranks]
         wave_of = {ci: wi for wi, wave in enumerate(waves) for ci, _ in wave}
         t_run0 = time.time()

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 from pi3_slam_b200 import ops  # noqa: E402
-from pi3_slam_b200.host.datasets import chunk_index_list, plan_waves, split_frames  # noqa: E402
+from pi3_slam_b200.host.datasets import chunk_index_list, nccl_high_priority_options, plan_waves, split_frames  # noqa: E402
 from pi3_slam_b200.offline_chunk_creator import OfflineChunkCreator, OfflineCreatorConfig  # noqa: E402
 from pi3_slam_b200.pi3 import Pi3  # noqa: E402
 from pi3_slam_b200.synthetic import make_frames, make_state_dict  # noqa: E402
@@ -118,7 +118,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    dist.init_process_group("nccl", device_id=dev, pg_options=nccl_high_priority_options())
     model = Pi3()
     model.load_state_dict(make_state_dict(0), strict=True)
     model = model.to(dev).eval()
