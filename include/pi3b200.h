@@ -151,6 +151,17 @@ int pi3b_keypoint_gather(void* stream, const float* points, const float* local_p
 int pi3b_sample_grid(void* stream, const float* local_points, const float* conf, const int* ys, const int* xs,
                      float* out_pts, uint8_t* out_valid, int N, int H, int W, int hs, int ws, float conf_thr);
 
+/* Batched focal / z-shift recovery: per frame n, the shift that minimises |f * xy / (z + shift) - uv| over the valid
+ * samples (f eliminated in closed form), by the algorithm scipy.optimize.least_squares(x0=0, ftol, method='lm') executes
+ * for one parameter (2-point finite differences + MINPACK lmder, mode 1, factor 100, <= 100 evaluations): the reference's
+ * result is defined by that solver's early stop. pts fp32 [N,S,3], valid uint8 [N,S], uv fp32 [S,2] (pi3b_sample_grid
+ * layout). out4[n] = (shift as fp32, focal at that shift, #function evaluations, #valid); fewer than 2 valid samples:
+ * (0, 1, 0, count).
+ * replaces: solve_optimal_focal_shift utils/geometry_numpy.py:79-96 looped over frames by recover_focal_shift
+ *   utils/geometry_torch.py:114-169 (host scipy, 67 ms per 100-frame chunk). */
+int pi3b_focal_shift_lm(void* stream, const float* pts, const uint8_t* valid, const float* uv, int N, int S, float ftol,
+                        float* out4);
+
 /* out2[0] = lower median of a[i*a_stride] / b[i*b_stride] over mask[i] != 0 (NaN if the mask is empty or any masked
  * ratio is NaN, as torch.median), out2[1] = count.
  * replaces: _get_scale_factor_for_pi3 slam/offline_chunk_creator.py:121-127 (boolean indexing + torch.median). */

@@ -58,6 +58,8 @@ SIGNATURES = {
     "pi3b_keypoint_gather": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int]),
     # stream, local_points, conf, ys, xs, out_pts, out_valid, N, H, W, hs, ws, conf_thr
     "pi3b_sample_grid": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float]),
+    # stream, pts, valid, uv, N, S, ftol, out4
+    "pi3b_focal_shift_lm": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, _P]),
     # stream, a, a_stride, b, b_stride, mask, n, out2
     "pi3b_median_ratio": (c_int, [_P, _P, c_int, _P, c_int, _P, c_int, _P]),
     # stream, qry, ref, valid, num_problems, n_per, out18

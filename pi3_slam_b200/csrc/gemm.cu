@@ -328,7 +328,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int mi = m_blk * kBlockM + quarter * 32 + (hi & 3) * 8 + (lane >> 2);
             if (mi < p.M) {
               const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
-              rq[hi] = *reinterpret_cast<const float4*>(p.resid + size_t(mo) * p.ld_resid + n0 + (hi >> 2) * 16 + (lane & 3) * 4);
+              rq[hi] = __ldcg(reinterpret_cast<const float4*>(p.resid + size_t(mo) * p.ld_resid + n0 + (hi >> 2) * 16 + (lane & 3) * 4));
             }
           }
         }
@@ -364,14 +364,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // fp32 read-modify-write of the residual stream: transpose through smem so that every global access is
             // 64 contiguous bytes per row instead of 32 different rows per instruction (32 L1 wavefronts each).
             // A/B on B200, fc2 + LayerScale + residual at M = 100400: 1203 -> 1284 TFLOP/s.
-            float* stg = reinterpret_cast<float*>(smem + S::STG_OFFSET + ew * S::STG_BYTES_PER_WARP);
+            // (explicit st.shared / ld.shared: pointers derived from the manually aligned smem base are generic to the
+            // compiler, which emitted generic ST.E / LD.E here)
+            const uint32_t stg = smem_u32(smem + S::STG_OFFSET + ew * S::STG_BYTES_PER_WARP);
             const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              float4* wr = reinterpret_cast<float4*>(stg + lane * S::STG_STRIDE);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                wr[j] = make_float4(v[h * 16 + 4 * j], v[h * 16 + 4 * j + 1], v[h * 16 + 4 * j + 2], v[h * 16 + 4 * j + 3]);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (lane * S::STG_STRIDE + 4 * j) * 4),
+                             "f"(v[h * 16 + 4 * j]), "f"(v[h * 16 + 4 * j + 1]), "f"(v[h * 16 + 4 * j + 2]),
+                             "f"(v[h * 16 + 4 * j + 3]) : "memory");
               __syncwarp();
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
@@ -379,7 +382,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int mi = m_blk * kBlockM + quarter * 32 + rr;
                 if (mi < p.M) {
                   const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
-                  float4 x = *reinterpret_cast<const float4*>(stg + rr * S::STG_STRIDE + sub_c);
+                  float4 x = qk_lds128(stg + (rr * S::STG_STRIDE + sub_c) * 4);
                   const int col = n0 + h * 16 + sub_c;
                   const float4 q = rq[h * 4 + it];
                   x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;

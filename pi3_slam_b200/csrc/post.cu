@@ -300,6 +300,224 @@ __global__ void __launch_bounds__(256) umeyama_kernel(const float* __restrict__ 
   o[17] = float(cnt);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Batched focal / z-shift recovery: per frame,  min_{shift} | f(shift) * xy / (z + shift) - uv |
+// with the focal eliminated in closed form — what utils/geometry_numpy.py:79-96 hands to
+// scipy.optimize.least_squares(x0=0, ftol=1e-3, method='lm'). The reference's RESULT is defined by that solver's early
+// stop (on degenerate geometry it returns after two evaluations), so this is a port of the algorithm scipy executes for
+// one parameter, not a generic optimiser: scipy's 2-point finite-difference Jacobian (step sqrt(eps)*sign(x)*max(1,|x|))
+// driving MINPACK lmder / lmpar / qrsolv with internal scaling (mode 1), factor 100, xtol = gtol = 1e-8, 100 evaluations
+// at most — oracle/lm_oracle.py is the same code in numpy and is pinned against scipy itself. For n = 1 every matrix is a
+// scalar (R = -|J|, Q^T f = -(J.f)/|J|); the only data-parallel work is the three reductions per function evaluation.
+// One block per frame, fp64, all threads walk the (uniform) control flow. out[n] = (shift, focal, nfev, #valid).
+// ------------------------------------------------------------------------------------------------
+struct LmData {
+  const float* pts;       // [S][3] of this frame
+  const uint8_t* valid;   // [S]
+  const float* uv;        // [S][2]
+  int S;
+};
+
+// focal that minimises the residual at `shift`: sum(xy_proj . uv) / sum(|xy_proj|^2)
+__device__ double lm_focal(const LmData& d, double shift, double* red) {
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < d.S; i += blockDim.x) {
+    if (!d.valid[i]) continue;
+    const double inv = 1.0 / (double(d.pts[i * 3 + 2]) + shift);
+    const double px = double(d.pts[i * 3 + 0]) * inv, py = double(d.pts[i * 3 + 1]) * inv;
+    a += px * double(d.uv[i * 2 + 0]) + py * double(d.uv[i * 2 + 1]);
+    b += px * px + py * py;
+  }
+  a = block_sum(a, red);
+  b = block_sum(b, red);
+  return a / b;
+}
+// |fvec|^2 at `shift`
+__device__ double lm_sqnorm(const LmData& d, double shift, double f, double* red) {
+  double q = 0.0;
+  for (int i = threadIdx.x; i < d.S; i += blockDim.x) {
+    if (!d.valid[i]) continue;
+    const double inv = 1.0 / (double(d.pts[i * 3 + 2]) + shift);
+    const double rx = f * double(d.pts[i * 3 + 0]) * inv - double(d.uv[i * 2 + 0]);
+    const double ry = f * double(d.pts[i * 3 + 1]) * inv - double(d.uv[i * 2 + 1]);
+    q += rx * rx + ry * ry;
+  }
+  return block_sum(q, red);
+}
+// forward-difference Jacobian column J = (fvec(x1) - fvec(x0)) / dx: returns |J|^2 and J . fvec(x0)
+__device__ void lm_jacobian(const LmData& d, double x0, double f0, double x1, double f1, double dx, double* red,
+                            double& jj, double& jf) {
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < d.S; i += blockDim.x) {
+    if (!d.valid[i]) continue;
+    const double z = double(d.pts[i * 3 + 2]), X = double(d.pts[i * 3 + 0]), Y = double(d.pts[i * 3 + 1]);
+    const double u = double(d.uv[i * 2 + 0]), v = double(d.uv[i * 2 + 1]);
+    const double i0 = 1.0 / (z + x0), i1 = 1.0 / (z + x1);
+    const double r0x = f0 * X * i0 - u, r0y = f0 * Y * i0 - v;
+    const double jx = ((f1 * X * i1 - u) - r0x) / dx, jy = ((f1 * Y * i1 - v) - r0y) / dx;
+    a += jx * jx + jy * jy;
+    b += jx * r0x + jy * r0y;
+  }
+  jj = block_sum(a, red);
+  jf = block_sum(b, red);
+}
+
+__device__ __forceinline__ void lm_qrsolv1(double r, double diag_in, double qtb, double& x, double& sdiag) {
+  double rn = r, wa = qtb;
+  if (diag_in != 0.0) {
+    double sn, cs;
+    if (fabs(r) < fabs(diag_in)) {
+      const double cotan = r / diag_in;
+      sn = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
+      cs = sn * cotan;
+    } else {
+      const double tn = diag_in / r;
+      cs = 0.5 / sqrt(0.25 + 0.25 * tn * tn);
+      sn = cs * tn;
+    }
+    rn = cs * r + sn * diag_in;
+    wa = cs * qtb;
+  }
+  sdiag = rn;
+  x = rn != 0.0 ? wa / rn : 0.0;
+}
+
+__device__ void lm_lmpar1(double r, double dg, double qtb, double delta, double& par, double& x) {
+  constexpr double kDwarf = 2.2250738585072014e-308;
+  x = r != 0.0 ? qtb / r : 0.0;
+  double dxnorm = fabs(dg * x);
+  double fp = dxnorm - delta;
+  if (fp <= 0.1 * delta) {
+    par = 0.0;
+    return;
+  }
+  double parl = 0.0;
+  if (r != 0.0) {
+    const double w = dg * (dg * x / dxnorm) / r;
+    parl = ((fp / delta) / fabs(w)) / fabs(w);
+  }
+  const double gnorm = fabs(r * qtb / dg);
+  double paru = gnorm / delta;
+  if (paru == 0.0) paru = kDwarf / fmin(delta, 0.1);
+  par = fmin(fmax(par, parl), paru);
+  if (par == 0.0) par = gnorm / dxnorm;
+  for (int it = 1;; ++it) {
+    if (par == 0.0) par = fmax(kDwarf, 0.001 * paru);
+    double sdiag;
+    lm_qrsolv1(r, sqrt(par) * dg, qtb, x, sdiag);
+    dxnorm = fabs(dg * x);
+    const double temp = fp;
+    fp = dxnorm - delta;
+    if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || it == 10) break;
+    const double w = dg * (dg * x / dxnorm) / sdiag;
+    const double parc = ((fp / delta) / fabs(w)) / fabs(w);
+    if (fp > 0.0) parl = fmax(parl, par);
+    if (fp < 0.0) paru = fmin(paru, par);
+    par = fmax(parl, par + parc);
+  }
+}
+
+__global__ void __launch_bounds__(256) focal_shift_lm_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ valid,
+                                                             const float* __restrict__ uv, int S, float ftol_f,
+                                                             float* __restrict__ out) {
+  __shared__ double red[8];
+  constexpr double kEps = 2.220446049250313e-16, kFactor = 100.0, kXtol = 1e-8, kGtol = 1e-8;
+  constexpr int kMaxFev = 100;
+  const double ftol = double(ftol_f);
+  const int n = blockIdx.x;
+  LmData d{pts + size_t(n) * S * 3, valid + size_t(n) * S, uv, S};
+  double cnt = 0.0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) cnt += d.valid[i] ? 1.0 : 0.0;
+  cnt = block_sum(cnt, red);
+  if (cnt < 2.0) {   // reference: focal 1, shift 0 when fewer than two valid samples (geometry_torch.py:150-154)
+    if (threadIdx.x == 0) { out[n * 4 + 0] = 0.f; out[n * 4 + 1] = 1.f; out[n * 4 + 2] = 0.f; out[n * 4 + 3] = float(cnt); }
+    return;
+  }
+  double x = 0.0;
+  double fx = lm_focal(d, x, red);
+  double fnorm = sqrt(lm_sqnorm(d, x, fx, red));
+  int nfev = 1, iter = 1, info = 0;
+  double par = 0.0, diag = 0.0, delta = 0.0, xnorm = 0.0;
+  while (info == 0) {
+    const double h = sqrt(kEps) * (x >= 0.0 ? 1.0 : -1.0) * fmax(1.0, fabs(x));
+    const double x1 = x + h;
+    const double dx = x1 - x;
+    const double f1 = lm_focal(d, x1, red);
+    double jj, jf;
+    lm_jacobian(d, x, fx, x1, f1, dx, red, jj, jf);
+    const double jnorm = sqrt(jj);
+    const double r = -jnorm;
+    const double qtf = jnorm != 0.0 ? -jf / jnorm : 0.0;
+    if (iter == 1) {
+      diag = jnorm != 0.0 ? jnorm : 1.0;
+      xnorm = fabs(diag * x);
+      delta = kFactor * xnorm;
+      if (delta == 0.0) delta = kFactor;
+    }
+    double gnorm = 0.0;
+    if (fnorm != 0.0 && jnorm != 0.0) gnorm = fabs(r * (qtf / fnorm) / jnorm);
+    if (gnorm <= kGtol) {
+      info = 4;
+      break;
+    }
+    diag = fmax(diag, jnorm);
+    for (;;) {
+      double p;
+      lm_lmpar1(r, diag, qtf, delta, par, p);
+      p = -p;
+      const double x_new = x + p;
+      const double pnorm = fabs(diag * p);
+      if (iter == 1) delta = fmin(delta, pnorm);
+      const double f_new = lm_focal(d, x_new, red);
+      const double fnorm1 = sqrt(lm_sqnorm(d, x_new, f_new, red));
+      ++nfev;
+      double actred = -1.0;
+      if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+      const double temp1 = fabs(r * p) / fnorm;
+      const double temp2 = sqrt(par) * pnorm / fnorm;
+      const double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
+      const double dirder = -(temp1 * temp1 + temp2 * temp2);
+      const double ratio = prered != 0.0 ? actred / prered : 0.0;
+      if (ratio <= 0.25) {
+        double temp = actred >= 0.0 ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
+        if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+        delta = temp * fmin(delta, pnorm / 0.1);
+        par /= temp;
+      } else if (par == 0.0 || ratio >= 0.75) {
+        delta = pnorm / 0.5;
+        par *= 0.5;
+      }
+      if (ratio >= 1e-4) {
+        x = x_new;
+        fx = f_new;
+        fnorm = fnorm1;
+        xnorm = fabs(diag * x);
+        ++iter;
+      }
+      const bool ftest = fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0;
+      if (ftest) info = 1;
+      if (delta <= kXtol * xnorm) info = 2;
+      if (ftest && info == 2) info = 3;
+      if (info != 0) break;
+      if (nfev >= kMaxFev) info = 5;
+      if (fabs(actred) <= kEps && prered <= kEps && 0.5 * ratio <= 1.0) info = 6;
+      if (delta <= kEps * xnorm) info = 7;
+      if (gnorm <= kEps) info = 8;
+      if (info != 0 || ratio >= 1e-4) break;
+    }
+  }
+  // the reference re-evaluates the focal at the fp32-rounded shift (geometry_numpy.py:91-94)
+  const float shift32 = float(x);
+  const double focal = lm_focal(d, double(shift32), red);
+  if (threadIdx.x == 0) {
+    out[n * 4 + 0] = shift32;
+    out[n * 4 + 1] = float(focal);
+    out[n * 4 + 2] = float(nfev);
+    out[n * 4 + 3] = float(cnt);
+  }
+}
+
 }  // namespace pi3b
 
 using namespace pi3b;
@@ -343,4 +561,12 @@ extern "C" int pi3b_umeyama_sim3_batched(void* stream, const float* qry, const f
   PI3B_REQUIRE(qry && ref && out18 && num_problems > 0 && n_per > 0, "pi3b_umeyama_sim3_batched: bad args");
   umeyama_kernel<<<num_problems, 256, 0, static_cast<cudaStream_t>(stream)>>>(qry, ref, valid, n_per, out18);
   return check_launch("umeyama launch");
+}
+
+extern "C" int pi3b_focal_shift_lm(void* stream, const float* pts, const uint8_t* valid, const float* uv, int N, int S,
+                                   float ftol, float* out4) {
+  PI3B_REQUIRE(pts && valid && uv && out4, "pi3b_focal_shift_lm: null pointer");
+  PI3B_REQUIRE(N > 0 && S > 0 && ftol > 0.f, "pi3b_focal_shift_lm: bad arguments");
+  focal_shift_lm_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(pts, valid, uv, S, ftol, out4);
+  return check_launch("focal_shift_lm launch");
 }

@@ -1,9 +1,10 @@
 """Per-frame focal / z-shift recovery and intrinsics (reference: utils/camera_estimation.py:12-132,
 utils/geometry_torch.py:39-51,114-169, utils/geometry_numpy.py:79-96).
 
-As in the reference this is host-side work: the device only gathers the 64x64 nearest-downsampled samples
-(N x 4096 x 3 floats instead of the dense maps), then each frame is a 1-D scipy Levenberg-Marquardt solve.
-SURVEY.md section 8f lists a batched GPU solver as a follow-up; it is not on this round's scope table.
+The device gathers the 64x64 nearest-downsampled samples (N x 4096 x 3 floats instead of the dense maps) and, by
+default, also runs the per-frame 1-parameter Levenberg-Marquardt solve (`pi3b_focal_shift_lm`, SURVEY.md section 8 row
+f3: the algorithm scipy executes, restated — 67 ms of serial host work per 100-frame chunk removed). The host scipy
+solve of the reference is kept as `solver="host"` (what the device solver is tested against).
 """
 from __future__ import annotations
 
@@ -89,14 +90,38 @@ def sample_for_intrinsics(local_points: torch.Tensor, conf: torch.Tensor,
     return pts, val, c[2]
 
 
+def solve_focal_shift_on_device(pts: torch.Tensor, valid: torch.Tensor, uv_lr: np.ndarray) -> torch.Tensor:
+    """Device half of the solve: fp32 [N, 4] = (shift, focal, nfev, #valid) per frame, still on the device."""
+    key = ("uv", id(uv_lr), str(pts.device))
+    uv_dev = _SAMPLE_CACHE.get(key)
+    if uv_dev is None:
+        uv_dev = torch.from_numpy(np.ascontiguousarray(uv_lr, dtype=np.float32)).to(pts.device)
+        _SAMPLE_CACHE[key] = uv_dev
+    return ops.focal_shift_lm(pts, valid, uv_dev, 1e-3)
+
+
+def camera_parameters_from_focal_shift(focal_np: np.ndarray, shift_np: np.ndarray, H: int, W: int,
+                                       device="cpu") -> Dict[str, torch.Tensor]:
+    """The reference's focal -> (fx, fy, cx, cy, K) formulas (camera_estimation.py:47-60). Returns the reference-shaped
+    dict: intrinsics (N,3,3); the rest (1,N)."""
+    N = focal_np.shape[0]
+    focal = torch.from_numpy(np.ascontiguousarray(focal_np, dtype=np.float32)).to(device).reshape(1, N)
+    shift = torch.from_numpy(np.ascontiguousarray(shift_np, dtype=np.float32)).to(device).reshape(1, N)
+    return _intrinsics_dict(focal, shift, H, W, device)
+
+
 def camera_parameters_from_samples(pts: np.ndarray, valid: np.ndarray, uv_lr: np.ndarray, H: int, W: int,
                                    device="cpu") -> Dict[str, torch.Tensor]:
-    """Host half: per-frame LM solve + the reference's focal -> (fx, fy, cx, cy, K) formulas
-    (camera_estimation.py:47-60). Returns the reference-shaped dict: intrinsics (N,3,3); the rest (1,N)."""
+    """Host solve (`solver="host"`): per-frame scipy LM, then the intrinsics formulas."""
     N = pts.shape[0]
     focal_np, shift_np = recover_focal_shift_from_samples(pts, valid.astype(bool), uv_lr)
     focal = torch.from_numpy(focal_np).to(device).reshape(1, N)
     shift = torch.from_numpy(shift_np).to(device).reshape(1, N)
+    return _intrinsics_dict(focal, shift, H, W, device)
+
+
+def _intrinsics_dict(focal: torch.Tensor, shift: torch.Tensor, H: int, W: int, device) -> Dict[str, torch.Tensor]:
+    N = focal.shape[1]
     aspect = W / H
     fx = focal / 2 * (1 + aspect ** 2) ** 0.5 / aspect * W
     fy = focal / 2 * (1 + aspect ** 2) ** 0.5 * H
@@ -113,9 +138,13 @@ def camera_parameters_from_samples(pts: np.ndarray, valid: np.ndarray, uv_lr: np
 
 
 def estimate_camera_parameters_single_chunk(local_points: torch.Tensor, conf: torch.Tensor,
-                                            downsample_size: Tuple[int, int] = (64, 64)) -> Dict[str, torch.Tensor]:
+                                            downsample_size: Tuple[int, int] = (64, 64),
+                                            solver: str = "device") -> Dict[str, torch.Tensor]:
     """local_points (N,H,W,3), conf (N,H,W,1) on the device -> dict like the reference's
     estimate_camera_parameters_single_chunk: intrinsics (N,3,3); focal/shift/fx/fy/cx/cy (1,N), on the device."""
     H, W = local_points.shape[1:3]
     pts, val, uv_lr = sample_for_intrinsics(local_points, conf, downsample_size)
-    return camera_parameters_from_samples(pts.cpu().numpy(), val.cpu().numpy(), uv_lr, H, W, device=local_points.device)
+    if solver == "host":
+        return camera_parameters_from_samples(pts.cpu().numpy(), val.cpu().numpy(), uv_lr, H, W, device=local_points.device)
+    sol = solve_focal_shift_on_device(pts, val, uv_lr).cpu().numpy()
+    return camera_parameters_from_focal_shift(sol[:, 1], sol[:, 0], H, W, device=local_points.device)

@@ -23,7 +23,8 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib, ops
-from .host.camera_estimation import camera_parameters_from_samples, sample_for_intrinsics
+from .host.camera_estimation import (camera_parameters_from_focal_shift, camera_parameters_from_samples,
+                                     sample_for_intrinsics, solve_focal_shift_on_device)
 from .host.datasets import ChunkImageDataset, nccl_high_priority_options, plan_waves, split_frames
 from .host.image_utils import calculate_target_size, load_images_u8, resize_u8_on_host
 from .host.keypoints import create_keypoint_extractor
@@ -50,6 +51,7 @@ class OfflineCreatorConfig:
     moge_model_path: Optional[str] = None   # local MoGe checkpoint (model.pt); None => hub id like the reference
     sequence_parallel_tail: bool = True     # multi-GPU: run the last (partial) wave of chunks sequence-parallel
     device_resize: bool = True              # loader threads only decode; Pillow-exact resize + ToTensor run on the GPU
+    intrinsics_solver: str = "device"       # 'device': pi3b_focal_shift_lm (scipy's 1-parameter LM restated); 'host': scipy
 
 
 class _PendingChunk:
@@ -75,8 +77,13 @@ class _PendingChunk:
         camera_params = None
         if self.intr is not None:
             try:
-                pts, val, uv_lr, H, W = self.intr
-                camera_params = camera_parameters_from_samples(pts.numpy(), val.numpy(), uv_lr, H, W)
+                if self.intr[0] == "device":      # (shift, focal, nfev, #valid) per frame, solved on the GPU
+                    _, sol, H, W = self.intr
+                    sol = sol.numpy()
+                    camera_params = camera_parameters_from_focal_shift(sol[:, 1], sol[:, 0], H, W)
+                else:
+                    _, pts, val, uv_lr, H, W = self.intr
+                    camera_params = camera_parameters_from_samples(pts.numpy(), val.numpy(), uv_lr, H, W)
             except Exception as e:
                 print(f"⚠️  Camera parameter estimation failed: {e}")
         result: Dict = {"camera_poses": self.staged["camera_poses"], "image_paths": self.chunk_paths,
@@ -299,7 +306,11 @@ class OfflineChunkCreator:
             if self.config.estimate_camera_params:
                 try:
                     pts, val, uv_lr = sample_for_intrinsics(pi3_result["local_points"][0], pi3_result["conf"][0])
-                    pend.intr = (stage(pts), stage(val), uv_lr, int(imgs_dev.shape[-2]), int(imgs_dev.shape[-1]))
+                    hw = (int(imgs_dev.shape[-2]), int(imgs_dev.shape[-1]))
+                    if self.config.intrinsics_solver == "host":
+                        pend.intr = ("host", stage(pts), stage(val), uv_lr) + hw
+                    else:
+                        pend.intr = ("device", stage(solve_focal_shift_on_device(pts, val, uv_lr))) + hw
                 except Exception as e:
                     print(f"⚠️  Camera parameter estimation failed: {e}")
             pend.staged["camera_poses"] = stage(pi3_result["camera_poses"][0])

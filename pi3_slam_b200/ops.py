@@ -361,6 +361,20 @@ def sample_grid(local_points, conf, ys, xs, conf_thr: float = 0.1):
     return pts, val
 
 
+def focal_shift_lm(pts: torch.Tensor, valid: torch.Tensor, uv: torch.Tensor, ftol: float = 1e-3) -> torch.Tensor:
+    """Per-frame focal / z-shift solve on the device (scipy's 1-parameter LM restated). pts fp32 [N,S,3], valid uint8
+    [N,S], uv fp32 [S,2]. Returns fp32 [N,4] = (shift, focal, nfev, #valid)."""
+    lib = _lib.load()
+    _req(pts, torch.float32, "pts"); _req(uv, torch.float32, "uv")
+    assert pts.is_contiguous() and valid.is_contiguous() and uv.is_contiguous() and valid.dtype == torch.uint8
+    N, S = pts.shape[:2]
+    assert valid.shape == (N, S) and uv.shape == (S, 2) and valid.is_cuda and uv.is_cuda
+    out = torch.empty(N, 4, device=pts.device)
+    rc = lib.pi3b_focal_shift_lm(_stream(), pts.data_ptr(), valid.data_ptr(), uv.data_ptr(), N, S, ftol, out.data_ptr())
+    _lib.check(rc, "pi3b_focal_shift_lm")
+    return out
+
+
 def median_ratio(a: torch.Tensor, b: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """Lower median of a/b over mask (1-D strided views allowed). Returns a 2-vector (median, count) on device."""
     lib = _lib.load()

@@ -169,6 +169,46 @@ def test_median_ratio_propagates_nan_like_torch():
     assert got[0].item() == (a[mk.bool()] / b[mk.bool()]).median().item()
 
 
+def test_device_lm_solver_matches_scipy_and_its_restatement():
+    """pi3b_focal_shift_lm against the reference's host solve (scipy least_squares 'lm') and against
+    oracle.lm_oracle on the same samples: same number of function evaluations, shift / focal within rtol 1e-4 — on
+    perspective-consistent clouds (several LM iterations), on degenerate ones (scipy's early stop after 2 evaluations
+    defines the reference result) and on frames with fewer than two valid samples."""
+    from oracle.lm_oracle import lm_focal_shift
+    from pi3_slam_b200 import ops
+    from pi3_slam_b200.host.camera_estimation import solve_optimal_focal_shift
+
+    rng = np.random.default_rng(1)
+    N, S = 12, 4096
+    uv = ((rng.random((S, 2)).astype(np.float32) - 0.5) * 1.2)
+    pts = np.zeros((N, S, 3), np.float32)
+    valid = np.zeros((N, S), np.uint8)
+    for n in range(N):
+        zt = rng.random(S).astype(np.float32) * 3 + 1.0
+        ft, true_shift = rng.random() * 1.5 + 0.4, rng.random() * 2 - 0.5
+        cloud = np.concatenate([uv * zt[:, None] / ft, (zt - true_shift)[:, None]], 1).astype(np.float32)
+        if n % 4 == 3:
+            cloud = rng.normal(0, 1, cloud.shape).astype(np.float32)          # degenerate: not a perspective cloud
+        else:
+            cloud += rng.normal(0, 0.01 * (n % 3), cloud.shape).astype(np.float32)
+        pts[n] = cloud
+        valid[n] = rng.random(S) > 0.25
+    valid[10] = 0
+    valid[10, 17] = 1                                                          # one valid sample -> (shift 0, focal 1)
+    valid[11] = 0
+    out = ops.focal_shift_lm(torch.from_numpy(pts).cuda(), torch.from_numpy(valid).cuda(), torch.from_numpy(uv).cuda()).cpu().numpy()
+    for n in range(N):
+        m = valid[n].astype(bool)
+        if m.sum() < 2:
+            assert out[n, 0] == 0.0 and out[n, 1] == 1.0 and out[n, 3] == m.sum()
+            continue
+        s_ref, f_ref = solve_optimal_focal_shift(uv[m], pts[n][m])
+        s_or, f_or, nfev = lm_focal_shift(uv[m], pts[n][m])
+        assert int(out[n, 2]) == nfev and int(out[n, 3]) == int(m.sum()), (n, out[n], nfev)
+        for got, want in ((out[n, 0], float(s_ref)), (out[n, 1], float(f_ref)), (out[n, 0], float(s_or)), (out[n, 1], float(f_or))):
+            assert abs(got - want) <= 1e-4 * max(abs(want), 1e-3), (n, out[n], s_ref, f_ref)
+
+
 def test_process_and_save_contract(model, tmp_path):
     from pi3_slam_b200.synthetic import make_frames
     creator = _creator(model, tmp_path, chunk_length=4, overlap=1, max_num_keypoints=25, keypoint_seed=11)

@@ -125,3 +125,39 @@ def test_rope2d_restatement_matches_the_reference_native_kernel_source():
     got = tok.clone()
     ref.rope_2d(got, pos, 100.0, 1.0)
     assert (got - want).abs().max().item() < 2e-5     # fp32 cosf/sinf/powf at angles up to 40 rad
+
+
+def test_lm_restatement_matches_scipy():
+    """oracle.lm_oracle (MINPACK lmder for one parameter, driven as scipy >= 1.16 drives it) against scipy itself: same
+    evaluation count, same shift / focal — on the degenerate geometry of the chunk golden (scipy stops after 2
+    evaluations) and on perspective-consistent clouds with noise (several LM iterations)."""
+    from functools import partial
+
+    import numpy as np
+    from scipy.optimize import least_squares
+
+    from oracle.lm_oracle import lm_focal_shift, residual
+
+    def scipy_solve(uv, xyz):
+        uv, xy, z = uv.reshape(-1, 2), xyz[..., :2].reshape(-1, 2), xyz[..., 2].reshape(-1)
+        sol = least_squares(partial(residual, uv, xy, z), x0=0, ftol=1e-3, method="lm")
+        s = sol["x"].squeeze().astype(np.float32)
+        xp = xy / (z + s)[:, None]
+        return s, (xp * uv).sum() / np.square(xp).sum(), sol.nfev
+
+    rng = np.random.default_rng(0)
+    for case in range(24):
+        S = int(rng.integers(50, 4096))
+        uv = (rng.random((S, 2)).astype(np.float32) - 0.5) * 1.2
+        zt = rng.random(S).astype(np.float32) * 3 + 1.0
+        ft = rng.random() * 1.5 + 0.4
+        true_shift = rng.random() * 2 - 0.5
+        xyz = np.concatenate([uv * zt[:, None] / ft, (zt - true_shift)[:, None]], 1).astype(np.float32)
+        if case % 3 == 2:
+            xyz = rng.normal(0, 1, xyz.shape).astype(np.float32)          # not a perspective cloud at all: degenerate
+        else:
+            xyz += rng.normal(0, 0.02 * (case % 4), xyz.shape).astype(np.float32)
+        a, b = scipy_solve(uv, xyz), lm_focal_shift(uv, xyz)
+        assert a[2] == b[2], (case, a, b)
+        assert abs(float(a[0]) - float(b[0])) <= 1e-5 * max(1.0, abs(float(a[0]))), (case, a, b)
+        assert abs(float(a[1]) - float(b[1])) <= 1e-5 * abs(float(a[1])), (case, a, b)
