@@ -22,8 +22,7 @@
 // each scheduler; S 3x64, O 3x64, P 3x32 TMEM columns (480 of 512); ONE ISSUER WARP PER TILE (with one issuer and grouped
 // waits the tiles ran in lockstep, their exponential phases coincided on the MUFU pipe: 645 vs 888 TFLOP/s,
 // profiles/r01_attn_rev8_ab.log); a softmax warp hands S back as soon as the scores are in registers (s_free) so QK(j+1)
-// runs under this step's exponentials; setmaxnreg 48/152 (budgets must add up to the launch allocation). The grid of a
-// long launch is tail-balanced: whole waves of three-tile CTAs, then the left-over rows as one-tile CTAs.
+// runs under this step's exponentials; setmaxnreg 48/152 (budgets must add up to the launch allocation).
 //
 // attn_fwd_kernel_t4 (kv_len <= 8192, frame-local layers): FOUR Q tiles, P written in place over the first 32 columns
 // of its own S tile (S/P 4x64 + O 4x64 = 512 columns), four softmax warps per scheduler, two issuer warps serving two
@@ -63,10 +62,9 @@ struct AttnParams {
   int ldo;
   float scale_log2;  // softmax scale * log2(e)
   float* lse;        // optional fp32 [num_heads][num_seqs * q_len]: max + log2(sum) of the scaled log2-domain scores
-  // work decomposition: blocks [0, n_full) own ROWS query rows each (blocks_full per (sequence, head), query block
-  // fastest so that neighbouring CTAs share one head's K/V in L2); blocks [n_full, grid) own 128 rows each (tail_per
-  // per (sequence, head)), starting at row blocks_full * ROWS
-  int blocks_full, n_full, tail_per;
+  // work decomposition: one block per (query block of ROWS rows, sequence, head), query block fastest so that
+  // neighbouring CTAs share one head's K/V in L2
+  int blocks_per_seq;
 };
 
 struct Work {
@@ -78,22 +76,12 @@ template <int ROWS>
 __device__ __forceinline__ Work decode_work(const AttnParams& p) {
   Work w;
   int item = blockIdx.x;
-  if (item < p.n_full) {
-    const int qb = item % p.blocks_full;
-    item /= p.blocks_full;
-    w.seq = item % p.num_seqs;
-    w.head = item / p.num_seqs;
-    w.q0 = qb * ROWS;
-    w.q_valid = min(ROWS, p.q_len - w.q0);
-  } else {
-    item -= p.n_full;
-    const int qb = item % p.tail_per;
-    item /= p.tail_per;
-    w.seq = item % p.num_seqs;
-    w.head = item / p.num_seqs;
-    w.q0 = p.blocks_full * ROWS + qb * 128;
-    w.q_valid = min(128, p.q_len - w.q0);
-  }
+  const int qb = item % p.blocks_per_seq;
+  item /= p.blocks_per_seq;
+  w.seq = item % p.num_seqs;
+  w.head = item / p.num_seqs;
+  w.q0 = qb * ROWS;
+  w.q_valid = min(ROWS, p.q_len - w.q0);
   return w;
 }
 
@@ -789,36 +777,11 @@ static int attn_launch(void* stream, const void* q, const void* k, const void* v
   p.lse = lse;
 
   const int dev = current_device();
-  // work decomposition (see AttnParams)
-  const int64_t groups = int64_t(num_seqs) * num_heads;
-  const int blocks_all = (q_len + rows_per_cta - 1) / rows_per_cta;
-  p.blocks_full = blocks_all;
-  p.tail_per = 0;
-  int64_t items = blocks_all * groups;
-  static const bool tail_ok = []() { const char* e = getenv("PI3B_ATTN_TAIL"); return !(e && e[0] == '0'); }();
-  if (tiles == 3 && tail_ok) {
-    // Long launch: a CTA runs for ~kv_len / 64 steps of ~1 us, so the last, partly filled wave costs a whole CTA time
-    // (2.4 % of the 28.3-wave cfg2 launch). Keep whole waves of three-tile CTAs and hand the left-over rows out as
-    // one-tile CTAs (measured cost of a one-tile CTA relative to a three-tile CTA: kSingleCost), if that is shorter.
-    const int num_sms = num_sms_of(dev);
-    constexpr double kSingleCost = 0.62;
-    const int64_t whole = int64_t(q_len / rows_per_cta) * groups;           // three-tile CTAs with all rows valid
-    const int64_t waves = whole / num_sms;
-    if (waves >= 2) {
-      const int keep = int(waves * num_sms / groups);                        // per (sequence, head)
-      const int left_rows = q_len - keep * rows_per_cta;
-      const int singles = (left_rows + 127) / 128;
-      const double plain = double((items + num_sms - 1) / num_sms);
-      const double split = double((keep * groups + num_sms - 1) / num_sms) +
-                           kSingleCost * double((singles * groups + num_sms - 1) / num_sms);
-      if (keep > 0 && singles > 0 && split < plain) {
-        p.blocks_full = keep;
-        p.tail_per = singles;
-        items = (int64_t(keep) + singles) * groups;
-      }
-    }
-  }
-  p.n_full = int(int64_t(p.blocks_full) * groups);
+  // (Handing the rows of the last, partly filled wave out as one-tile CTAs was measured and dropped: no gain at 28.3 waves,
+  // profiles/r02_attn_poly_ab.log "@tail0", and the one-tile CTAs of all 16 heads run together, re-streaming every head's
+  // K/V from DRAM: +0.4 GB per launch.)
+  p.blocks_per_seq = (q_len + rows_per_cta - 1) / rows_per_cta;
+  const int64_t items = int64_t(p.blocks_per_seq) * num_seqs * num_heads;
   PI3B_REQUIRE(items < (1ll << 31), "pi3b_attn_fwd_hd64: too many work items");
 
   CUtensorMap tmQ, tmK, tmV;

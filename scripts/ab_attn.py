@@ -40,7 +40,7 @@ def main():
     libs = sorted(glob.glob(os.path.join(ROOT, "pi3_slam_b200/build/variants/*.so")))
     if only:
         libs = [l for l in libs if os.path.basename(l)[:-3] in only.split(",")]
-    # ENVS="name:K=V,K2=V2;name2:..." runs each library once more per named environment (e.g. PI3B_ATTN_TAIL=0)
+    # ENVS="name:K=V,K2=V2;name2:..." runs each library once more per named environment (e.g. PI3B_ATTN_TILES=4)
     envsets = [("", {})]
     for spec in filter(None, os.environ.get("ENVS", "").split(";")):
         nm, kv = spec.split(":", 1)

@@ -28,7 +28,7 @@ C = H * 64
 def sampled_rows(S: int, n: int = 600) -> torch.Tensor:
     g = torch.Generator().manual_seed(S)
     fixed = list(range(0, 40)) + [127, 128, 129, 383, 384, 385, 511, 512, 513] + list(range(S - 40, S))
-    # last (partial) three-tile and four-tile blocks and the tail-balanced one-tile CTAs all sit at the end of the sequence
+    # the last (partial) three-tile and four-tile query blocks sit at the end of the sequence
     fixed += list(range(S - 700, S - 40, 16))
     rest = torch.randint(0, S, (n - len(fixed),), generator=g).tolist()
     return torch.tensor(sorted(set(fixed + rest)), dtype=torch.long)
@@ -92,7 +92,7 @@ def test_attention_at_chunk_global_sizes_each_kernel_forced(tiles):
         "from test_scale_parity_gpu import check_attention\n"
         "print('RESULT', json.dumps([check_attention(S, m) for S in (64300, 100400) for m in ('spread', 'rising')]))\n"
     ) % (ROOT, os.path.join(ROOT, "tests"))
-    env = dict(os.environ, PI3B_ATTN_TILES=str(tiles), PI3B_ATTN_TAIL="0" if tiles == 3 else "1")
+    env = dict(os.environ, PI3B_ATTN_TILES=str(tiles))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     import json
