@@ -69,6 +69,18 @@ int pi3b_attn_fwd_hd64_lse(void* stream, const void* q, const void* k, const voi
                            int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo, float* lse,
                            int num_seqs, int q_len, int kv_len, int num_heads, float scale);
 
+/* pi3b_attn_fwd_hd64 / _lse (lse may be NULL) with a caller-provided scratch buffer: workspace (device, 4-byte aligned,
+ * >= 4 * num_seqs * num_heads bytes; NULL = none). With it, sequences longer than 8192 keys run the BOUNDED-REFERENCE
+ * softmax: one streaming pass over K finds max |k|^2 per (sequence, head), |q| max|k| * scale bounds every score of a
+ * row, and the softmax is evaluated against that fixed reference instead of tracking the running maximum (identical
+ * mathematics, within rounding; rows whose bound would be looser than 2^100 stay on the online path). The workspace
+ * must not be shared by calls running concurrently on different streams.
+ * replaces: the same call sites as pi3b_attn_fwd_hd64. */
+int pi3b_attn_fwd_hd64_ws(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
+                          int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo, float* lse,
+                          int num_seqs, int q_len, int kv_len, int num_heads, float scale, void* workspace,
+                          int64_t workspace_bytes);
+
 /* out[row, 64h + c] = sum_i w_i(row, h) * parts[i][row, 64h + c], w_i = 2^(lses[i] - max_i) / sum_i 2^(lses[i] - max_i):
  * exact combination of n_parts (1..4) attention results computed over disjoint key/value sets. parts: HOST array of
  * n_parts device pointers to bf16 [rows, 64*num_heads] (row pitch ld_part); lses: HOST array of device pointers to fp32

@@ -32,6 +32,9 @@ SIGNATURES = {
     # stream, q, k, v, ldq, ldk, ldv, q_col0, k_col0, v_col0, out, ldo, lse, num_seqs, q_len, kv_len, num_heads, scale
     "pi3b_attn_fwd_hd64_lse": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64, _P,
                                        c_int, c_int, c_int, c_int, c_float]),
+    # ... as pi3b_attn_fwd_hd64_lse (lse nullable) ..., workspace, workspace_bytes
+    "pi3b_attn_fwd_hd64_ws": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64, _P,
+                                      c_int, c_int, c_int, c_int, c_float, _P, c_int64]),
     # stream, n_parts, parts(host void*[n]), lses(host float*[n]), ld_part, out, ldo, lse_out, rows, num_heads
     "pi3b_attn_merge": (c_int, [_P, c_int, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int]),
     # stream, x, ldx, gamma, beta, eps, out, ldo, out_f32, M, D, override_rows, period, n_override

@@ -40,12 +40,14 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace pi3b {
 
 // ---- exponential mix (compile-time; A/B'd through -D on the same box) -----------------------------------------------
 // Of every 8 column pairs, PI3B_POLY_PAIRS compute BOTH exponentials with the packed polynomial (share = PAIRS/8).
 #ifndef PI3B_POLY_PAIRS
-#define PI3B_POLY_PAIRS 2
+#define PI3B_POLY_PAIRS 3
 #endif
 #ifndef PI3B_POLY_DEG
 #define PI3B_POLY_DEG 2
@@ -62,6 +64,9 @@ struct AttnParams {
   int ldo;
   float scale_log2;  // softmax scale * log2(e)
   float* lse;        // optional fp32 [num_heads][num_seqs * q_len]: max + log2(sum) of the scaled log2-domain scores
+  // optional fp32 [num_seqs][num_heads]: max over the sequence's keys of |k|^2 (kmax2_kernel). Enables the bounded-
+  // reference softmax of the three-tile kernel: |q . k| <= |q| max|k| is an a-priori upper bound of every score of a row
+  const float* kmax2;
   // work decomposition: one block per (query block of ROWS rows, sequence, head), query block fastest so that
   // neighbouring CTAs share one head's K/V in L2
   int blocks_per_seq;
@@ -268,6 +273,62 @@ __device__ __forceinline__ void tma_producer(uint8_t* smem_q, uint8_t* smem_k, u
 __device__ __forceinline__ void softmax_release_fence() { tc_fence_before(); }
 
 // =====================================================================================================================
+// Bounded-reference softmax (three-tile kernel, long sequences). Online softmax spends, per 64-key step and row, a
+// 33-instruction FMNMX3 chain, the lazy-rescale vote and ~250 clocks of serial latency on tracking the running maximum.
+// Softmax is invariant to the reference, so ANY upper bound of the row's scores that is not absurdly loose will do:
+// Cauchy-Schwarz gives m_ref = |q| * max_j |k_j| * scale (exact in fp32 up to rounding, margin added). max_j |k_j|^2 per
+// (sequence, head) comes from one streaming pass over K (kmax2_kernel, 206 MB at 100 400 keys, ~40 us); |q|^2 from the
+// row's 64 values already in shared memory. Safety: the first step still runs the online code and yields m_lo <= true
+// maximum; the fixed reference is only adopted when m_ref - m_lo <= 100 for every row of the warp (then the dominant
+// terms are >= 2^-100, far from fp32 / bf16 underflow); otherwise the warp simply stays on the online path.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) kmax2_kernel(const __nv_bfloat16* __restrict__ k, int64_t ldk, int k_col0,
+                                                    int kv_len, int num_heads, float* __restrict__ kmax2) {
+  __shared__ int smax[64];
+  const int seq = blockIdx.y;
+  if (threadIdx.x < 64) smax[threadIdx.x] = 0;
+  __syncthreads();
+  const int sub = threadIdx.x & 7;                       // 8 lanes x 16 bytes = the 64 channels of one (row, head)
+  const int64_t units = int64_t(kv_len) * num_heads;
+  for (int64_t u = int64_t(blockIdx.x) * 32 + (threadIdx.x >> 3); u < units; u += int64_t(gridDim.x) * 32) {
+    const int row = int(u / num_heads), head = int(u % num_heads);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(k + (int64_t(seq) * kv_len + row) * ldk + k_col0 + head * 64 + sub * 8));
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float lo = __uint_as_float(w4[i] << 16), hi = __uint_as_float(w4[i] & 0xffff0000u);
+      q = fmaf(lo, lo, fmaf(hi, hi, q));
+    }
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 4);
+    if (sub == 0) atomicMax(&smax[head], __float_as_int(q));   // non-negative floats order like their bit patterns
+  }
+  __syncthreads();
+  if (threadIdx.x < num_heads) atomicMax(reinterpret_cast<int*>(kmax2) + seq * num_heads + threadIdx.x, smax[threadIdx.x]);
+}
+
+// |q_row|^2 of this thread's query row from the SWIZZLE_128B Q tile in shared memory (128 bytes per row; the order of
+// the 16-byte chunks does not matter for a sum of squares; lanes start at different chunks to spread the banks)
+__device__ __forceinline__ float q_row_sqnorm(uint32_t q_tile_saddr, int row) {
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t a, b, cc, d;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a), "=r"(b), "=r"(cc), "=r"(d) : "r"(q_tile_saddr + row * 128 + (((c + row) & 7) << 4)));
+    const uint32_t w4[4] = {a, b, cc, d};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float lo = __uint_as_float(w4[i] << 16), hi = __uint_as_float(w4[i] & 0xffff0000u);
+      q = fmaf(lo, lo, fmaf(hi, hi, q));
+    }
+  }
+  return q;
+}
+
+// =====================================================================================================================
 // Three-tile kernel (kv_len > 8192)
 // =====================================================================================================================
 constexpr int kA3Threads = 512;
@@ -459,10 +520,56 @@ attn_fwd_kernel_t3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
       };
+      // The same step with a FIXED reference m_used (bounded-reference softmax, see above): no row maximum, no rescale vote.
+      auto step_fixed = [&](const int j, const uint64_t negm2, auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
+        if (!s_ready) mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        uint32_t sr[64];
+        tmem_ld_x32(tm_s, sr);
+        tmem_ld_x32(tm_s + 32, sr + 32);
+        tmem_ld_wait();
+        softmax_release_fence();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+        const bool pv_ready = mbar_try_wait(&pv_done[t], (j - 1) & 1);
+        if (MASK) mask_tail<64>(sr, 0, p.kv_len - j * 64);
+        exp_block<64>(sr, sc2, negm2, lsum);
+        s_ready = !MASK && mbar_try_wait(&s_full[t], (j + 1) & 1);
+        if (!pv_ready) mbar_wait(&pv_done[t], (j - 1) & 1);
+        tc_fence_after();
+        tmem_st_x32(tm_p, sr);
+        tmem_st_wait();
+        softmax_release_fence();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      };
+
       // loop bounds are compared against p.kv_len (constant bank) so that no register is held for the trip count
       int j = 0;
-      for (; (j + 1) * 64 < p.kv_len; ++j) step(j, FalseTag{});
-      step(j, TrueTag{});   // last step: columns past kv_len (if any) are masked to -inf
+      bool fixed = false;
+      if (p.kmax2 != nullptr && p.kv_len > 64) {
+        // a-priori bound of this row's scores (log2 domain), with a margin for the fp32 rounding of norms and products
+        mbar_wait(q_full, 0);
+        const float q2 = q_row_sqnorm(smem_u32(smem + Attn3Smem::Q_OFF + t * kTileBytes), quarter * 32 + lane);
+        const float m_ref = sqrtf(q2 * __ldg(p.kmax2 + w.seq * p.num_heads + w.head)) * sc * 1.001f + 0.0625f;
+        step(0, FalseTag{});                        // online first step: m_used = maximum of the first 64 scores <= true maximum
+        j = 1;
+        fixed = __all_sync(0xffffffffu, m_ref - m_used <= 100.0f);
+        if (fixed) {                                // move the reference up to the bound: O(0) and the row sum are rescaled once
+          mbar_wait(&pv_done[t], 0);
+          tc_fence_after();
+          rescale_row(true, m_ref, m_used, lsum, tm_o);
+        }
+      }
+      if (fixed) {
+        const uint64_t negm2 = pack2(-m_used, -m_used);
+        for (; (j + 1) * 64 < p.kv_len; ++j) step_fixed(j, negm2, FalseTag{});
+        step_fixed(j, negm2, TrueTag{});
+      } else {
+        for (; (j + 1) * 64 < p.kv_len; ++j) step(j, FalseTag{});
+        step(j, TrueTag{});   // last step: columns past kv_len (if any) are masked to -inf
+      }
 
       mbar_wait(&pv_done[t], j & 1);
       tc_fence_after();
@@ -747,7 +854,7 @@ using namespace pi3b;
 
 static int attn_launch(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                        int q_col0, int k_col0, int v_col0, void* out, int64_t ldo, float* lse, int num_seqs, int q_len,
-                       int kv_len, int num_heads, float scale) {
+                       int kv_len, int num_heads, float scale, void* workspace = nullptr, int64_t workspace_bytes = 0) {
   PI3B_REQUIRE(q && k && v && out, "pi3b_attn_fwd_hd64: null pointer");
   PI3B_REQUIRE(num_seqs > 0 && q_len > 0 && kv_len > 0 && num_heads > 0, "pi3b_attn_fwd_hd64: bad shape");
   PI3B_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
@@ -775,6 +882,7 @@ static int attn_launch(void* stream, const void* q, const void* k, const void* v
   p.ldo = (int)ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
+  p.kmax2 = nullptr;
 
   const int dev = current_device();
   // (Handing the rows of the last, partly filled wave out as one-tile CTAs was measured and dropped: no gain at 28.3 waves,
@@ -798,6 +906,19 @@ static int attn_launch(void* stream, const void* q, const void* k, const void* v
     if (cudaFuncSetAttribute(attn_fwd_kernel_t4, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Smem::TOTAL) != cudaSuccess)
       return check_launch("attn: cudaFuncSetAttribute (t4)");
     configured.done(dev);
+  }
+  // bounded-reference softmax (three-tile kernel): needs max |k|^2 per (sequence, head) in the caller's workspace
+  static const bool bounded_ok = []() { const char* e = getenv("PI3B_ATTN_BOUNDED"); return !(e && e[0] == '0'); }();
+  if (tiles == 3 && bounded_ok && workspace != nullptr && num_heads <= 64 && kv_len > 64 &&
+      workspace_bytes >= int64_t(num_seqs) * num_heads * 4 && (reinterpret_cast<uintptr_t>(workspace) & 3) == 0) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(workspace, 0, size_t(num_seqs) * num_heads * 4, st) != cudaSuccess) return check_launch("attn: memset");
+    const int64_t units = int64_t(kv_len) * num_heads;
+    const unsigned gx = unsigned(std::min<int64_t>((units + 31) / 32, int64_t(num_sms_of(dev)) * 8));
+    kmax2_kernel<<<dim3(gx, num_seqs), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(k), ldk, k_col0, kv_len, num_heads,
+                                                     static_cast<float*>(workspace));
+    if (int rc2 = check_launch("kmax2 launch")) return rc2;
+    p.kmax2 = static_cast<const float*>(workspace);
   }
   if (tiles == 4)
     attn_fwd_kernel_t4<<<(unsigned)items, kA4Threads, Attn4Smem::TOTAL, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
@@ -847,4 +968,12 @@ extern "C" int pi3b_attn_merge(void* stream, int n_parts, const void* const* par
   const int64_t threads = int64_t(rows) * num_heads * 8;
   attn_merge_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("attn merge launch");
+}
+
+extern "C" int pi3b_attn_fwd_hd64_ws(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk,
+                                     int64_t ldv, int q_col0, int k_col0, int v_col0, void* out, int64_t ldo, float* lse,
+                                     int num_seqs, int q_len, int kv_len, int num_heads, float scale, void* workspace,
+                                     int64_t workspace_bytes) {
+  return attn_launch(stream, q, k, v, ldq, ldk, ldv, q_col0, k_col0, v_col0, out, ldo, lse, num_seqs, q_len, kv_len,
+                     num_heads, scale, workspace, workspace_bytes);
 }

@@ -92,6 +92,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
     return out
 
 
+_ATTN_WS = {}
+
+
+def _attn_workspace(device: torch.device) -> torch.Tensor:
+    """Scratch buffer of the attention launches (max |k|^2 per (sequence, head) for the bounded-reference softmax): one per
+    (device, stream), because launches on different streams may run concurrently."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ATTN_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(16384, device=device, dtype=torch.float32)
+        _ATTN_WS[key] = ws
+    return ws
+
+
 def gemm_qkv(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor], num_heads: int,
              qk_norm: Optional[torch.Tensor], eps: float, cs_table: Optional[torch.Tensor], tokens_per_frame: int,
              n_special: int, patch_w: int) -> torch.Tensor:
@@ -134,9 +148,11 @@ def attention_qkv(qkv: torch.Tensor, out: torch.Tensor, num_seqs: int, seq_len: 
     assert qkv.dim() == 2 and qkv.shape[1] == 3 * C and qkv.stride(1) == 1
     assert qkv.shape[0] == num_seqs * seq_len and out.shape[0] == qkv.shape[0] and out.shape[1] == C
     ld = qkv.stride(0)
-    rc = lib.pi3b_attn_fwd_hd64(_stream(), qkv.data_ptr(), qkv.data_ptr(), qkv.data_ptr(), ld, ld, ld, 0, C, 2 * C,
-                                out.data_ptr(), out.stride(0), num_seqs, seq_len, seq_len, num_heads, scale)
-    _lib.check(rc, "pi3b_attn_fwd_hd64")
+    ws = _attn_workspace(qkv.device)
+    rc = lib.pi3b_attn_fwd_hd64_ws(_stream(), qkv.data_ptr(), qkv.data_ptr(), qkv.data_ptr(), ld, ld, ld, 0, C, 2 * C,
+                                   out.data_ptr(), out.stride(0), None, num_seqs, seq_len, seq_len, num_heads, scale,
+                                   ws.data_ptr(), ws.numel() * 4)
+    _lib.check(rc, "pi3b_attn_fwd_hd64_ws")
     return out
 
 
@@ -150,10 +166,11 @@ def attention_q_kv(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, num_seq
     C = num_heads * 64
     assert q.stride(1) == 1 and kv.stride(1) == 1 and out.stride(1) == 1
     assert q.shape[0] == num_seqs * q_len and kv.shape == (num_seqs * kv_len, 2 * C) and out.shape == (q.shape[0], C)
-    rc = lib.pi3b_attn_fwd_hd64(_stream(), q.data_ptr(), kv.data_ptr(), kv.data_ptr(), q.stride(0), kv.stride(0),
-                                kv.stride(0), q_col0, 0, C, out.data_ptr(), out.stride(0), num_seqs, q_len, kv_len,
-                                num_heads, scale)
-    _lib.check(rc, "pi3b_attn_fwd_hd64")
+    ws = _attn_workspace(q.device)
+    rc = lib.pi3b_attn_fwd_hd64_ws(_stream(), q.data_ptr(), kv.data_ptr(), kv.data_ptr(), q.stride(0), kv.stride(0),
+                                   kv.stride(0), q_col0, 0, C, out.data_ptr(), out.stride(0), None, num_seqs, q_len, kv_len,
+                                   num_heads, scale, ws.data_ptr(), ws.numel() * 4)
+    _lib.check(rc, "pi3b_attn_fwd_hd64_ws")
     return out
 
 
@@ -168,10 +185,11 @@ def attention_q_kv_lse(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, lse
     assert q.stride(1) == 1 and kv.stride(1) == 1 and out.stride(1) == 1 and lse.is_contiguous()
     assert q.shape[0] == num_seqs * q_len and kv.shape[0] == num_seqs * kv_len and kv.shape[1] == 2 * C
     assert out.shape == (q.shape[0], C) and lse.shape == (num_heads, q.shape[0])
-    rc = lib.pi3b_attn_fwd_hd64_lse(_stream(), q.data_ptr(), kv.data_ptr(), kv.data_ptr(), q.stride(0), kv.stride(0),
-                                    kv.stride(0), q_col0, 0, C, out.data_ptr(), out.stride(0), lse.data_ptr(), num_seqs,
-                                    q_len, kv_len, num_heads, scale)
-    _lib.check(rc, "pi3b_attn_fwd_hd64_lse")
+    ws = _attn_workspace(q.device)
+    rc = lib.pi3b_attn_fwd_hd64_ws(_stream(), q.data_ptr(), kv.data_ptr(), kv.data_ptr(), q.stride(0), kv.stride(0),
+                                   kv.stride(0), q_col0, 0, C, out.data_ptr(), out.stride(0), lse.data_ptr(), num_seqs,
+                                   q_len, kv_len, num_heads, scale, ws.data_ptr(), ws.numel() * 4)
+    _lib.check(rc, "pi3b_attn_fwd_hd64_ws")
 
 
 def attention_merge(parts, lses, out: torch.Tensor, num_heads: int = 16, lse_out: Optional[torch.Tensor] = None):

@@ -132,3 +132,29 @@ def test_lse_and_merge_over_key_blocks(S, H, splits):
     one = torch.empty_like(out)
     ops.attention_merge(parts[:1], lses[:1], one, H)
     assert torch.equal(one, parts[0])
+
+
+@pytest.mark.parametrize("outlier", [0.0, 60.0])
+def test_bounded_reference_softmax_and_its_fallback(outlier):
+    """Sequences longer than 8192 keys run the bounded-reference softmax (reference = |q| max|k| scale instead of the
+    running maximum). outlier = 0: the bound is tight enough and the fixed reference is adopted. outlier = 60: one key
+    with a 60x larger norm makes the Cauchy-Schwarz bound ~500 (log2 units) above the typical scores, so the warps must
+    stay on the online path — both against an fp64 softmax on sampled rows."""
+    from pi3_slam_b200 import ops
+
+    S, H = 9100, 2
+    torch.manual_seed(7)
+    qkv = torch.randn(S, 3 * H * 64, device="cuda")
+    if outlier:
+        qkv[S - 3, H * 64: 2 * H * 64] *= outlier          # the outlier key sits in the LAST tile: the first tile cannot see it
+    qkv = qkv.bfloat16()
+    out = torch.full((S, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attention_qkv(qkv, out, 1, S, H)
+    rows = torch.arange(0, S, 13, device="cuda")
+    q, k, v = qkv.double().view(S, 3, H, 64).permute(1, 2, 0, 3)
+    ref = (torch.softmax(q[:, rows] @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).permute(1, 0, 2).reshape(len(rows), H * 64)
+    assert torch.isfinite(out.float()).all()
+    err = (out[rows].double() - ref).norm() / ref.norm()
+    assert err.item() < 1e-2, f"rel err {err.item():.3e}"
+    worst = ((out[rows].double() - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+    assert worst < 3e-2, worst
