@@ -290,20 +290,25 @@ __global__ void __launch_bounds__(256) kmax2_kernel(const __nv_bfloat16* __restr
   __syncthreads();
   const int sub = threadIdx.x & 7;                       // 8 lanes x 16 bytes = the 64 channels of one (row, head)
   const int64_t units = int64_t(kv_len) * num_heads;
-  for (int64_t u = int64_t(blockIdx.x) * 32 + (threadIdx.x >> 3); u < units; u += int64_t(gridDim.x) * 32) {
-    const int row = int(u / num_heads), head = int(u % num_heads);
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(k + (int64_t(seq) * kv_len + row) * ldk + k_col0 + head * 64 + sub * 8));
-    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+  // block-uniform trip count (the shuffles below need every lane of the warp): out-of-range groups contribute 0
+  for (int64_t u0 = int64_t(blockIdx.x) * 32; u0 < units; u0 += int64_t(gridDim.x) * 32) {
+    const int64_t u = u0 + (threadIdx.x >> 3);
+    const bool in_range = u < units;
+    const int row = in_range ? int(u / num_heads) : 0, head = in_range ? int(u % num_heads) : 0;
     float q = 0.f;
+    if (in_range) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(k + (int64_t(seq) * kv_len + row) * ldk + k_col0 + head * 64 + sub * 8));
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float lo = __uint_as_float(w4[i] << 16), hi = __uint_as_float(w4[i] & 0xffff0000u);
-      q = fmaf(lo, lo, fmaf(hi, hi, q));
+      for (int i = 0; i < 4; ++i) {
+        const float lo = __uint_as_float(w4[i] << 16), hi = __uint_as_float(w4[i] & 0xffff0000u);
+        q = fmaf(lo, lo, fmaf(hi, hi, q));
+      }
     }
     q += __shfl_xor_sync(0xffffffffu, q, 1);
     q += __shfl_xor_sync(0xffffffffu, q, 2);
     q += __shfl_xor_sync(0xffffffffu, q, 4);
-    if (sub == 0) atomicMax(&smax[head], __float_as_int(q));   // non-negative floats order like their bit patterns
+    if (sub == 0 && in_range) atomicMax(&smax[head], __float_as_int(q));   // non-negative floats order like their bit patterns
   }
   __syncthreads();
   if (threadIdx.x < num_heads) atomicMax(reinterpret_cast<int*>(kmax2) + seq * num_heads + threadIdx.x, smax[threadIdx.x]);
