@@ -912,7 +912,9 @@ static int attn_launch(void* stream, const void* q, const void* k, const void* v
       return check_launch("attn: cudaFuncSetAttribute (t4)");
     configured.done(dev);
   }
-  // bounded-reference softmax (three-tile kernel): needs max |k|^2 per (sequence, head) in the caller's workspace
+  // bounded-reference softmax (three-tile kernel): needs max |k|^2 per (sequence, head) in the caller's workspace.
+  // (Measured and not kept for the four-tile kernel: at S = 1004 the pre-pass costs more than the dropped row-maximum
+  // pass saves, 0.617 vs 0.595 ms; at S = 100 400 it ties with the three-tile kernel — profiles/r02_attn_poly_ab.log "t4b".)
   static const bool bounded_ok = []() { const char* e = getenv("PI3B_ATTN_BOUNDED"); return !(e && e[0] == '0'); }();
   if (tiles == 3 && bounded_ok && workspace != nullptr && num_heads <= 64 && kv_len > 64 &&
       workspace_bytes >= int64_t(num_seqs) * num_heads * 4 && (reinterpret_cast<uintptr_t>(workspace) & 3) == 0) {
