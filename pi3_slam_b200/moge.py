@@ -11,7 +11,7 @@ The computation is a flat schedule of C-ABI launches (libpi3b200.so), no nn.Conv
   ConvStack channels-last fp32 maps [H*W, C]; 1x1 conv = GEMM; 3x3 replicate conv = pi3b_im2col3x3 (GroupNorm + ReLU
             fused into the gather) + GEMM with the residual add fused in the epilogue; ConvTranspose 2x2 = GEMM whose
             blocked output the next im2col reads in place; the uv concat of every level = pi3b_uv_affine
-  outputs   pi3b_resample2d (bilinear) -> pi3b_moge_remap; infer: 64x64 samples -> host scipy LM (as the reference,
+  outputs   pi3b_resample2d (bilinear) -> pi3b_moge_remap; infer: 64x64 samples -> pi3b_focal_shift_lm (the reference's scipy LM, restated;
             moge/utils/geometry_torch.py:115-170) -> pi3b_moge_depth
 
 Numerics: bf16 tensor-core operands, fp32 accumulation, fp32 maps / residuals / GroupNorm statistics (fp64 sums); the
@@ -427,12 +427,13 @@ class MoGeModel(nn.Module):
             # 64x64 nearest samples of (points, mask > 0.5) -> host LM over the z shift (geometry_torch.py:141-162)
             if "mask_logit" in o:
                 s_pts, s_val = ops.sample_grid(pts.unsqueeze(0), o["mask_logit"].unsqueeze(0), sc["ys"], sc["xs"], 0.5)
-                valid = s_val.cpu().numpy().astype(bool)
             else:
                 zeros = torch.zeros(1, H, W, device=pts.device)
                 s_pts, _ = ops.sample_grid(pts.unsqueeze(0), zeros, sc["ys"], sc["xs"], 0.5)
-                valid = np.ones((1, s_pts.shape[1]), dtype=bool)
-            focal, shift = camest.recover_focal_shift_from_samples(s_pts.cpu().numpy(), valid, sc["uv_lr"])
+                s_val = torch.ones(1, s_pts.shape[1], device=pts.device, dtype=torch.uint8)
+            # the 1-parameter LM solve on the device (pi3b_focal_shift_lm: the algorithm scipy executes, restated)
+            sol = camest.solve_focal_shift_on_device(s_pts, s_val, sc["uv_lr"]).cpu().numpy()
+            shift, focal = sol[:, 0], sol[:, 1]
             depth, mask = ops.moge_depth(pts, o.get("mask"), float(shift[0]), o.get("log_scale"), apply_mask)
             f = float(focal[0])
             K = torch.zeros(3, 3, device=pts.device)

@@ -27,6 +27,18 @@ for name, N, K, act, resid in [("qkv", 3072, 1024, 0, False), ("proj", 1024, 102
         o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         ours.append(lambda a=a, w=w, b=b, o=o, act=act: ops.gemm(a, w, o, bias=b, act=act))
     ref.append(lambda a=a, w=w, bb=bb: torch.nn.functional.linear(a, w, bb))
+# the decoder's fused QKV projection (q/k LayerNorm + RoPE in the epilogue)
+T, pw = 1004, 37
+qkn = torch.cat([torch.rand(64, device=dev) + 0.5, torch.randn(64, device=dev) * 0.1, torch.rand(64, device=dev) + 0.5,
+                 torch.randn(64, device=dev) * 0.1]).contiguous()
+inv_freq = 1.0 / (100.0 ** (torch.arange(0, 32, 2).float() / 32))
+ang = torch.einsum("i,j->ij", torch.arange(pw + 2, dtype=torch.float32), inv_freq)
+cs = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous().to(dev)
+a_q = torch.randn(M, 1024, device=dev).bfloat16()
+w_q = (torch.randn(3072, 1024, device=dev) * 0.02).bfloat16()
+b_q = torch.randn(3072, device=dev)
+o_q = torch.empty(M, 3072, device=dev, dtype=torch.bfloat16)
+ours.append(lambda: ops.gemm_qkv(a_q, w_q, o_q, b_q, 16, qkn, 1e-5, cs, T, 5, pw))
 for _ in range(reps):
     for f in ours:
         f()
