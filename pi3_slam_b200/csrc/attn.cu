@@ -54,6 +54,7 @@ namespace pi3b {
 #endif
 
 
+
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
 constexpr int kKvBytes = 64 * 128;     // 64 rows x 64 bf16
 
@@ -147,10 +148,10 @@ __device__ __forceinline__ void poly_exp2_x2(uint64_t x, float& p0, float& p1) {
 
 // ---- pieces shared by both kernels ----------------------------------------------------------------------------------
 
-// exponentials of NCOL scores held in registers: a[c] (fp32 bit patterns) -> packed bf16 P in a[0 .. NCOL/2), row sum
+// exponentials of NCOL scores held in registers: a[c] (fp32 bit patterns) -> packed bf16 P in out[0 .. NCOL/2), row sum
 // accumulated in the packed pair `lsum`. x = score * scale_log2 - m_used.
 template <int NCOL>
-__device__ __forceinline__ void exp_block(uint32_t* a, uint64_t sc2, uint64_t negm2, uint64_t& lsum) {
+__device__ __forceinline__ void exp_block(const uint32_t* a, uint32_t* out, uint64_t sc2, uint64_t negm2, uint64_t& lsum) {
 #pragma unroll
   for (int c = 0; c < NCOL; c += 2) {
     const uint64_t x = ffma2(pack2(__uint_as_float(a[c]), __uint_as_float(a[c + 1])), sc2, negm2);
@@ -166,7 +167,7 @@ __device__ __forceinline__ void exp_block(uint32_t* a, uint64_t sc2, uint64_t ne
       p1 = fast_exp2(x1);
     }
     lsum = fadd2(lsum, pack2(p0, p1));
-    a[c >> 1] = pack_bf16x2(p0, p1);
+    out[c >> 1] = pack_bf16x2(p0, p1);   // out may alias a: element c >> 1 <= c has already been consumed
   }
 }
 
@@ -513,7 +514,7 @@ attn_fwd_kernel_t3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
 
         const uint64_t negm2 = pack2(-m_used, -m_used);
-        exp_block<64>(sr, sc2, negm2, lsum);
+        exp_block<64>(sr, sr, sc2, negm2, lsum);
         // early poll of the next S tile: QK(j+1) was issued when s_free(j) arrived, ~a whole math phase ago
         s_ready = !MASK && mbar_try_wait(&s_full[t], (j + 1) & 1);
         // P_t was last read by PV(j-1): that MMA must have completed before the buffer is overwritten
@@ -537,9 +538,10 @@ attn_fwd_kernel_t3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         softmax_release_fence();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[t]);
-        const bool pv_ready = mbar_try_wait(&pv_done[t], (j - 1) & 1);
         if (MASK) mask_tail<64>(sr, 0, p.kv_len - j * 64);
-        exp_block<64>(sr, sc2, negm2, lsum);
+        // (moving the two polls into the middle of the exponentials measured no gain: profiles/r02_attn_poly_ab.log "mid2")
+        const bool pv_ready = mbar_try_wait(&pv_done[t], (j - 1) & 1);
+        exp_block<64>(sr, sr, sc2, negm2, lsum);
         s_ready = !MASK && mbar_try_wait(&s_full[t], (j + 1) & 1);
         if (!pv_ready) mbar_wait(&pv_done[t], (j - 1) & 1);
         tc_fence_after();
@@ -766,7 +768,7 @@ attn_fwd_kernel_t4(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tmem_ld_x32(tm_s + h * 32, a);
           tmem_ld_wait();
           if (MASK) mask_tail<32>(a, h * 32, kv_valid);
-          exp_block<32>(a, sc2, negm2, lsum);
+          exp_block<32>(a, a, sc2, negm2, lsum);
           // P half h goes to columns [16h, 16h+16); the other half's scores (columns 32..63) are still intact
           tmem_st_x16(tm_s + h * 16, a);
         }
