@@ -347,14 +347,20 @@ def cfg5_sp_extra(model, dev, rank, world) -> dict:
     ag_ms = e0.elapsed_time(e1) / 5
     fl = Pi3.flops(frames, H, W)
     ex = torch.tensor([sum(exposed) / max(1, len(exposed))], device=dev, dtype=torch.float64)
+    ex_min = ex.clone()
     dist.all_reduce(ex, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ex_min, op=dist.ReduceOp.MIN)
     layer_ms = (fl["global_attn"] / 18 / world) / 1e9 / 900.0     # a global layer's attention at ~900 TFLOP/s per GPU
     res.update(ms_per_chunk=ms, frames_per_s=frames / (ms * 1e-3),
                tflops_per_gpu=fl["total"] / (ms * 1e-3) / 1e12 / world, ms_per_chunk_blocking_allgather=ms_blocking,
                allgather_ms_per_layer=ag_ms,
                allgather_recv_bytes_per_rank_per_layer=(world - 1) * m_max * 4096,
                allgather_gbs_per_rank=(world - 1) * m_max * 4096 / (ag_ms * 1e-3) / 1e9,
+               # time the stream waits for the gathered K/V after the local-block attention. MAX over ranks includes the
+               # wait of the ranks that hold one frame less for the others (load imbalance of an uneven split); MIN over
+               # ranks (the most loaded rank) is the transfer time the local block really failed to hide
                exposed_allgather_ms_per_layer=float(ex.item()),
+               exposed_allgather_ms_per_layer_most_loaded_rank=float(ex_min.item()),
                exposed_share_of_global_layer=float(ex.item()) / (layer_ms + float(ex.item())))
     # correctness on a small shape: blocking variant bit-identical to the single-GPU forward, overlapped within tolerance
     n_small = 2 * world
