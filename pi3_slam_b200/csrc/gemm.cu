@@ -266,6 +266,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         *reinterpret_cast<float4*>(gamma_s + lane * 4) = g4;
       }
       __syncwarp();
+      // Residual slice of one 32-column chunk in the transposed (coalesced) lane layout: 8 x 16-byte loads per lane.
+      // The residual does not depend on the accumulator, so chunk 0 is requested BEFORE the accumulator wait (its DRAM
+      // latency hides under the main loop) and chunk c+1 right after chunk c's values have been consumed (under chunk
+      // c's stores and chunk c+1's TMEM read): the RMW epilogue was latency-bound with the loads issued per chunk.
+      float4 rq[8];
+      auto load_resid = [&](int c) {
+        const int n0c = n_blk * BLOCK_N + half * COLS_PER_WARP + c * 32;
+        if (QK || p.resid == nullptr || !p.vec_ok || c >= COLS_PER_WARP / 32 || n0c + 32 > p.N) return;
+#pragma unroll
+        for (int hi = 0; hi < 8; ++hi) {
+          const int mi = m_blk * kBlockM + quarter * 32 + (hi & 3) * 8 + (lane >> 2);
+          if (mi < p.M) {
+            const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
+            rq[hi] = __ldcg(reinterpret_cast<const float4*>(p.resid + size_t(mo) * p.ld_resid + n0c + (hi >> 2) * 16 + (lane & 3) * 4));
+          }
+        }
+      };
+      load_resid(0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (QK) {
@@ -317,21 +335,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n0 = n_blk * BLOCK_N + col_in_tile;
         if (n0 >= p.N) break;  // warp-uniform
         const int nvalid = min(32, p.N - n0);
-        // residual slice of this chunk in the transposed (coalesced) lane layout, requested before the accumulator
-        // chunk is read from TMEM: 8 x 16-byte loads in flight per lane (the RMW epilogue was latency-bound at
-        // 2.4 TB/s with 4 in flight and the loads issued after the math)
-        float4 rq[8];
-        const bool resid_fast = p.resid != nullptr && nvalid == 32 && p.vec_ok;
-        if (resid_fast) {
-#pragma unroll
-          for (int hi = 0; hi < 8; ++hi) {
-            const int mi = m_blk * kBlockM + quarter * 32 + (hi & 3) * 8 + (lane >> 2);
-            if (mi < p.M) {
-              const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
-              rq[hi] = __ldcg(reinterpret_cast<const float4*>(p.resid + size_t(mo) * p.ld_resid + n0 + (hi >> 2) * 16 + (lane & 3) * 4));
-            }
-          }
-        }
         uint32_t r[32];
         tmem_ld_x32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N + col_in_tile, r);
         tmem_ld_wait();
@@ -368,6 +371,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // compiler, which emitted generic ST.E / LD.E here)
             const uint32_t stg = smem_u32(smem + S::STG_OFFSET + ew * S::STG_BYTES_PER_WARP);
             const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
+            float4 xs[8];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -378,22 +382,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               __syncwarp();
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
-                const int rr = it * 8 + sub_r;
-                const int mi = m_blk * kBlockM + quarter * 32 + rr;
-                if (mi < p.M) {
-                  const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
-                  float4 x = qk_lds128(stg + (rr * S::STG_STRIDE + sub_c) * 4);
-                  const int col = n0 + h * 16 + sub_c;
-                  const float4 q = rq[h * 4 + it];
-                  x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
-                  if (p.out_f32)
-                    *reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(mo) * p.ldo + col) = x;
-                  else
-                    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + size_t(mo) * p.ldo + col) =
-                        make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-                }
+                float4 x = qk_lds128(stg + ((it * 8 + sub_r) * S::STG_STRIDE + sub_c) * 4);
+                const float4 q = rq[h * 4 + it];
+                x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+                xs[h * 4 + it] = x;
               }
               __syncwarp();
+            }
+            load_resid(c + 1);   // rq is free again: the next chunk's residual travels while this chunk is stored
+#pragma unroll
+            for (int hi = 0; hi < 8; ++hi) {
+              const int mi = m_blk * kBlockM + quarter * 32 + (hi & 3) * 8 + sub_r;
+              if (mi < p.M) {
+                const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
+                const int col = n0 + (hi >> 2) * 16 + sub_c;
+                const float4 x = xs[hi];
+                if (p.out_f32)
+                  *reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(mo) * p.ldo + col) = x;
+                else
+                  *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + size_t(mo) * p.ldo + col) =
+                      make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+              }
             }
           } else if (row_ok) {
             if (p.out_f32) {
