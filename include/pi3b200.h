@@ -187,6 +187,19 @@ int pi3b_median_ratio(void* stream, const float* a, int a_stride, const float* b
 int pi3b_umeyama_sim3_batched(void* stream, const float* qry, const float* ref, const uint8_t* valid,
                               int num_problems, int n_per, float* out18);
 
+/* Stage-2 front end: reprojection of a chunk's keypoints into neighbouring views + image-bounds test, as one flat,
+ * reference-ordered observation list. points fp32 [N,K,3] (world); w2t fp64 [N,16] = inverse camera poses (row-major,
+ * computed by the caller as the reference does); kmat fp64 [N,9] intrinsics or NULL (normalised coordinates);
+ * pairs int32 [R,2] = (source frame, target frame) in the reference's loop order. For pair r the keypoints k whose
+ * projection (u, v) satisfies 0 <= u < width, 0 <= v < height are emitted in keypoint order. Scratch: row_uv fp64 [R,K,2],
+ * row_kp int32 [R,K], row_count int32 [R]. Outputs: row_offset int32 [R+1] (row_offset[R] = number of observations) and,
+ * for o < min(total, capacity): obs_src, obs_kp, obs_view (int32) and obs_xy (fp64 [.,2]).
+ * replaces: the per-keypoint Python loops of ChunkPTRecon.create_recon_from_chunk utils/chunk_reconstruction.py:158-185
+ *   (_project_points_to_other_cams :445-479, _project_3d_points_to_camera :481-509); pytheia only receives the list. */
+int pi3b_project_observations(void* stream, const float* points, const double* w2t, const double* kmat, const int* pairs,
+                              int R, int K, double width, double height, double* row_uv, int* row_kp, int* row_count,
+                              int* row_offset, int* obs_src, int* obs_kp, int* obs_view, double* obs_xy, int capacity);
+
 /* ---- MoGe metric-depth pass (row a15): dense-prediction pieces around pi3b_gemm. Feature maps are channels-last
  * fp32 matrices [H*W, C] (row pitch ld, in elements). ---------------------------------------------------------- */
 

@@ -6,7 +6,7 @@ PyTorch is only used by callers for device memory and streams; nothing torch-typ
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 from pathlib import Path
 
 import os as _os
@@ -63,6 +63,9 @@ SIGNATURES = {
     "pi3b_sample_grid": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float]),
     # stream, pts, valid, uv, N, S, ftol, out4
     "pi3b_focal_shift_lm": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, _P]),
+    # stream, points, w2t, kmat, pairs, R, K, width, height, row_uv, row_kp, row_count, row_offset, obs_src, obs_kp, obs_view, obs_xy, capacity
+    "pi3b_project_observations": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_double, c_double, _P, _P, _P, _P, _P, _P, _P,
+                                          _P, c_int]),
     # stream, a, a_stride, b, b_stride, mask, n, out2
     "pi3b_median_ratio": (c_int, [_P, _P, c_int, _P, c_int, _P, c_int, _P]),
     # stream, qry, ref, valid, num_problems, n_per, out18

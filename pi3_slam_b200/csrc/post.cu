@@ -518,6 +518,106 @@ __global__ void __launch_bounds__(256) focal_shift_lm_kernel(const float* __rest
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Stage-2 front end: the reprojection of every keypoint of a chunk into its neighbouring views
+// and the image-bounds test that ChunkPTRecon.create_recon_from_chunk runs as Python loops
+// (utils/chunk_reconstruction.py:158-185 with _project_3d_points_to_camera :494-509): for a (source frame, target frame)
+// pair, X_cam = W2T_target [X 1], p = X_cam / X_cam.z, (u, v) = (K_target p).xy (or p.xy without intrinsics), kept when
+// 0 <= u < W and 0 <= v < H. fp64 like the reference's numpy (world-to-target inverses are computed by the caller exactly
+// as the reference does, numpy.linalg.inv in fp32). One block per pair; the in-bounds keypoints of the pair are written
+// COMPACTED AND IN KEYPOINT ORDER (ballot + prefix), so that the observation list keeps the reference's AddObservation
+// order. A second launch scans the per-pair counts and scatters the rows into one flat list.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) project_observations_kernel(const float* __restrict__ points, const double* __restrict__ w2t,
+                                                                   const double* __restrict__ kmat, const int* __restrict__ pairs,
+                                                                   int K, double W, double H, double* __restrict__ row_uv,
+                                                                   int* __restrict__ row_kp, int* __restrict__ row_count) {
+  __shared__ int warp_cnt[4];
+  __shared__ int base_s;
+  const int r = blockIdx.x;
+  const int src = pairs[2 * r], dst = pairs[2 * r + 1];
+  const double* T = w2t + size_t(dst) * 16;
+  const double* Km = kmat ? kmat + size_t(dst) * 9 : nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < K; k0 += blockDim.x) {
+    const int k = k0 + threadIdx.x;
+    bool inb = false;
+    double u = 0.0, v = 0.0;
+    if (k < K) {
+      const float* P = points + (size_t(src) * K + k) * 3;
+      const double x = double(P[0]), y = double(P[1]), z = double(P[2]);
+      const double cx = T[0] * x + T[1] * y + T[2] * z + T[3];
+      const double cy = T[4] * x + T[5] * y + T[6] * z + T[7];
+      const double cz = T[8] * x + T[9] * y + T[10] * z + T[11];
+      const double px = cx / cz, py = cy / cz, pz = cz / cz;
+      if (Km) {
+        u = Km[0] * px + Km[1] * py + Km[2] * pz;
+        v = Km[3] * px + Km[4] * py + Km[5] * pz;
+      } else {
+        u = px;
+        v = py;
+      }
+      inb = (0.0 <= u) && (u < W) && (0.0 <= v) && (v < H);   // NaN / inf (cz == 0) compare false, as in the reference
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, inb);
+    if (lane == 0) warp_cnt[warp] = __popc(ball);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (inb) {
+      const int pos = off + __popc(ball & ((1u << lane) - 1u));
+      row_uv[(size_t(r) * K + pos) * 2 + 0] = u;
+      row_uv[(size_t(r) * K + pos) * 2 + 1] = v;
+      row_kp[size_t(r) * K + pos] = k;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base_s += warp_cnt[0] + warp_cnt[1] + warp_cnt[2] + warp_cnt[3];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) row_count[r] = base_s;
+}
+
+// exclusive scan of the per-pair counts (single block; R is a few thousand) -> row_offset[0..R]
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int* __restrict__ cnt, int R, int* __restrict__ off) {
+  __shared__ int part[1024];
+  const int per = (R + blockDim.x - 1) / blockDim.x;
+  const int lo = threadIdx.x * per, hi = min(R, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += cnt[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < blockDim.x; ++i) { const int t = part[i]; part[i] = run; run += t; }
+    off[R] = run;
+  }
+  __syncthreads();
+  int run = part[threadIdx.x];
+  for (int i = lo; i < hi; ++i) { off[i] = run; run += cnt[i]; }
+}
+
+__global__ void __launch_bounds__(128) scatter_observations_kernel(const double* __restrict__ row_uv, const int* __restrict__ row_kp,
+                                                                   const int* __restrict__ row_count, const int* __restrict__ row_offset,
+                                                                   const int* __restrict__ pairs, int K, int capacity,
+                                                                   int* __restrict__ obs_src, int* __restrict__ obs_kp,
+                                                                   int* __restrict__ obs_view, double* __restrict__ obs_xy) {
+  const int r = blockIdx.x;
+  const int n = row_count[r], o0 = row_offset[r];
+  const int src = pairs[2 * r], dst = pairs[2 * r + 1];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int o = o0 + i;
+    if (o >= capacity) return;
+    obs_src[o] = src;
+    obs_kp[o] = row_kp[size_t(r) * K + i];
+    obs_view[o] = dst;
+    obs_xy[size_t(o) * 2 + 0] = row_uv[(size_t(r) * K + i) * 2 + 0];
+    obs_xy[size_t(o) * 2 + 1] = row_uv[(size_t(r) * K + i) * 2 + 1];
+  }
+}
+
 }  // namespace pi3b
 
 using namespace pi3b;
@@ -569,4 +669,21 @@ extern "C" int pi3b_focal_shift_lm(void* stream, const float* pts, const uint8_t
   PI3B_REQUIRE(N > 0 && S > 0 && ftol > 0.f, "pi3b_focal_shift_lm: bad arguments");
   focal_shift_lm_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(pts, valid, uv, S, ftol, out4);
   return check_launch("focal_shift_lm launch");
+}
+
+extern "C" int pi3b_project_observations(void* stream, const float* points, const double* w2t, const double* kmat,
+                                         const int* pairs, int R, int K, double width, double height, double* row_uv,
+                                         int* row_kp, int* row_count, int* row_offset, int* obs_src, int* obs_kp,
+                                         int* obs_view, double* obs_xy, int capacity) {
+  PI3B_REQUIRE(points && w2t && pairs && row_uv && row_kp && row_count && row_offset && obs_src && obs_kp && obs_view && obs_xy,
+               "pi3b_project_observations: null pointer");
+  PI3B_REQUIRE(R > 0 && K > 0 && capacity > 0, "pi3b_project_observations: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  project_observations_kernel<<<R, 128, 0, st>>>(points, w2t, kmat, pairs, K, width, height, row_uv, row_kp, row_count);
+  if (int rc = check_launch("project_observations launch")) return rc;
+  scan_counts_kernel<<<1, 1024, 0, st>>>(row_count, R, row_offset);
+  if (int rc = check_launch("scan_counts launch")) return rc;
+  scatter_observations_kernel<<<R, 128, 0, st>>>(row_uv, row_kp, row_count, row_offset, pairs, K, capacity, obs_src, obs_kp,
+                                                 obs_view, obs_xy);
+  return check_launch("scatter_observations launch");
 }

@@ -209,6 +209,51 @@ def test_device_lm_solver_matches_scipy_and_its_restatement():
             assert abs(got - want) <= 1e-4 * max(abs(want), 1e-3), (n, out[n], s_ref, f_ref)
 
 
+def _synthetic_chunk_for_recon(N, K, W, H, seed):
+    """A geometrically plausible chunk: points in front of a ring of cameras looking at them, fp16-stored like a chunk
+    file, so that a large share of the reprojections land inside the image (and a share outside / behind)."""
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.randn(N, K, 3, generator=g) * torch.tensor([1.5, 1.0, 1.0]) + torch.tensor([0.0, 0.0, 5.0])
+    poses = torch.eye(4).repeat(N, 1, 1)
+    for i in range(N):
+        a = 0.08 * (i - N / 2)
+        poses[i, :3, :3] = torch.tensor([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], dtype=torch.float32)
+        poses[i, :3, 3] = torch.tensor([0.3 * (i - N / 2), 0.02 * i, 0.0])
+    intr = torch.tensor([[0.9 * W, 0, W / 2], [0, 0.9 * W, H / 2], [0, 0, 1.0]]).repeat(N, 1, 1)
+    return {"points": pts.half(), "colors": (torch.rand(N, K, 3, generator=g) * 255).half(),
+            "keypoints": (torch.rand(N, K, 2, generator=g) * torch.tensor([W - 1.0, H - 1.0])).half(),
+            "camera_poses": poses, "intrinsics": intr, "original_width": W, "original_height": H}
+
+
+@pytest.mark.parametrize("case", ["golden5", "golden2", "synthetic", "no_intrinsics"])
+def test_stage2_observation_list_matches_oracle(case):
+    """pi3b_project_observations: the observation list of ChunkPTRecon.create_recon_from_chunk — same
+    tracks, same observations in the same order (membership of every reprojection = the reference's bounds test),
+    coordinates to 1e-9 — against oracle.recon_oracle, which is pinned bit-exactly to the real reference."""
+    from oracle.recon_oracle import observation_list
+    from pi3_slam_b200.reconstruction import chunk_observations
+
+    if case.startswith("golden"):
+        chunk = torch.load(os.path.join(GOLDEN, "chunk_tiny.pt"), weights_only=False)["chunk"]
+        max_obs = int(case[-1])
+    else:
+        chunk = _synthetic_chunk_for_recon(40, 200, 406, 308, 3)
+        max_obs = 5
+        if case == "no_intrinsics":
+            del chunk["intrinsics"]
+            chunk["original_width"], chunk["original_height"] = 1, 1     # normalised coordinates: a unit window
+    want = observation_list(chunk, max_obs)
+    got = chunk_observations(chunk, max_obs)
+    assert np.array_equal(got["track_point"], want["track_point"]) and np.array_equal(got["track_color"], want["track_color"])
+    assert np.array_equal(got["obs_view"], want["obs_view"]) and np.array_equal(got["obs_track"], want["obs_track"])
+    assert np.abs(got["obs_xy"] - want["obs_xy"]).max() < 1e-9 * max(1.0, np.abs(want["obs_xy"]).max())
+    N, K = chunk["keypoints"].shape[:2]
+    assert len(want["obs_view"]) > N * K          # some reprojections are kept ...
+    if not case.startswith("golden"):
+        n_pairs = sum(len(range(f)) + min(max_obs // 2, N - 1 - f) for f in range(N))
+        assert len(want["obs_view"]) < N * K + n_pairs * K   # ... and some are rejected
+
+
 def test_process_and_save_contract(model, tmp_path):
     from pi3_slam_b200.synthetic import make_frames
     creator = _creator(model, tmp_path, chunk_length=4, overlap=1, max_num_keypoints=25, keypoint_seed=11)

@@ -161,3 +161,23 @@ def test_lm_restatement_matches_scipy():
         assert a[2] == b[2], (case, a, b)
         assert abs(float(a[0]) - float(b[0])) <= 1e-5 * max(1.0, abs(float(a[0]))), (case, a, b)
         assert abs(float(a[1]) - float(b[1])) <= 1e-5 * abs(float(a[1])), (case, a, b)
+
+
+def test_recon_observation_list_restatement_matches_reference_golden():
+    """oracle.recon_oracle (the stage-2 front end's track / observation construction) against the calls the REAL
+    reference made on a recording pytheia stand-in (tests/golden/recon_tiny.pt, oracle/make_golden_recon.py)."""
+    import os
+
+    import numpy as np
+    import torch
+
+    from oracle.recon_oracle import observation_list
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    chunk = torch.load(os.path.join(root, "tests", "golden", "chunk_tiny.pt"), weights_only=False)["chunk"]
+    gold = torch.load(os.path.join(root, "tests", "golden", "recon_tiny.pt"), weights_only=False)["cases"]
+    for max_obs, ref in gold.items():
+        mine = observation_list(chunk, max_obs)
+        for k in ref:
+            assert np.array_equal(ref[k], mine[k]), (max_obs, k)
+    assert len(gold[5]["obs_view"]) > len(gold[2]["obs_view"]) > 120
