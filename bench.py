@@ -376,6 +376,17 @@ def cfg5_sp_extra(model, dev, rank, world) -> dict:
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     res["small_shape_blocking_bit_identical_to_1gpu"] = bool(flag[0].item() == 1.0)
     res["small_shape_overlapped_max_rel_l2"] = -float(flag[1].item())
+    # ... and at the FULL cfg5 shape: every rank also runs the whole 300-frame chunk alone (it fits one GPU: ~10 GB) and
+    # compares its own frames of the sequence-parallel result with that single-GPU forward
+    del small, ref, o1, o2
+    sp_out = {k: v.clone() for k, v in model(fr, sp_group=dist.group.WORLD, sp_frame_counts=counts).items()}
+    whole = make_frames(frames, H, W)[None].to(dev)
+    one = model(whole)
+    errs = {k: float((sp_out[k].double() - one[k][:, first:first + cnt].double()).norm() /
+                     one[k][:, first:first + cnt].double().norm()) for k in sp_out}
+    e = torch.tensor([errs[k] for k in sorted(errs)], device=dev, dtype=torch.float64)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    res["full_shape_sp_vs_1gpu_max_rel_l2"] = dict(zip(sorted(errs), e.tolist()))
     return res
 
 
