@@ -239,7 +239,17 @@ def cfg3_sequence_extra(model, dev, rank, world) -> dict:
     frames, H, W = 1000, 308, 406
     paths = [f"/synthetic/{i:05d}.png" for i in range(frames)]
     index = {p: i for i, p in enumerate(paths)}
-    loader = lambda ps, ts: torch.cat([make_frames(1, *ts, start_index=index[p]) for p in ps])  # noqa: E731
+    # The sequence as a decoder would hand it over: uint8 frames at the SOURCE resolution (640x480, 7-Scenes-shaped), held
+    # in host memory and materialised before the timed region (synthesising 1000 random frames costs more host time than
+    # decoding them would and is not part of the workload). The creator copies the bytes to the device and runs the
+    # Pillow-exact resize to the 308x406 target + ToTensor there (pi3b_resize_u8_pil), its real input path.
+    g = torch.Generator().manual_seed(4321)
+    source = torch.randint(0, 256, (frames, 480, 640, 3), dtype=torch.uint8, generator=g)
+
+    def loader(ps, ts):
+        i0 = index[ps[0]]
+        assert [index[p] for p in ps] == list(range(i0, i0 + len(ps)))
+        return source[i0:i0 + len(ps)]
     box = [tempfile.mkdtemp(prefix="pi3b_cfg3_")]
     if world > 1:
         dist.broadcast_object_list(box, src=0)
@@ -285,8 +295,9 @@ def cfg3_sequence_extra(model, dev, rank, world) -> dict:
         done = [s["chunk_done_s"].get(ci) for s in stats for ci, _ in wave if s["chunk_done_s"].get(ci) is not None]
         wave_done.append(max(done) if done else None)
     processed = sum(min(100, frames - 80 * i) for i in range(13))
-    return {"workload": "cfg3: 1000 frames 308x406, chunk 100 / overlap 20 (13 chunks, 1240 processed frames), grid "
-                        "keypoints 200, intrinsics solve, chunk files written", "n_gpus": world,
+    return {"workload": "cfg3: 1000 uint8 640x480 frames in host memory -> device resize to 308x406, chunk 100 / overlap 20 "
+                        "(13 chunks, 1240 processed frames), grid keypoints 200, intrinsics solve, chunk files written",
+            "n_gpus": world,
             "makespan_s": makespan, "sequence_frames_per_s": frames / makespan,
             "processed_frames_per_s": processed / makespan,
             "waves": [[len(r) for _, r in w] for w in waves], "wave_done_s": wave_done,

@@ -72,3 +72,29 @@ def test_plan_waves_properties():
     assert sum(n for _, n in split_frames(300, 8)) == 300 and split_frames(3, 2) == [(0, 2), (2, 1)]
     # fewer frames than ranks: the group shrinks
     assert plan_waves([2], 4) == [[(0, (0, 1))]]
+
+
+def test_sequence_parallel_gather_plan_compacts_remote_rows(monkeypatch):
+    """Pi3._sp_plan: the row moves that make every OTHER rank's K|V rows contiguous in the gathered (padded) buffer —
+    even and uneven frame splits, every rank position. Pure host logic: emulated on a CPU tensor."""
+    import torch
+    import torch.distributed as dist
+
+    from pi3_slam_b200.pi3 import Pi3
+
+    for counts in ([2, 2], [38, 38, 38, 38, 37, 37, 37, 37], [3, 2, 2], [1, 1, 1, 1], [5, 4], [2, 2, 2, 1], [4, 4, 3, 3, 3, 3, 3, 3]):
+        for r in range(len(counts)):
+            monkeypatch.setattr(dist, "get_world_size", lambda group=None, n=len(counts): n)
+            monkeypatch.setattr(dist, "get_rank", lambda group=None, rr=r: rr)
+            T = 3
+            sp = Pi3._sp_plan(None, counts, T)
+            m = sp["m_max"]
+            assert m == max(counts) * T and sp["all_rows"] == sum(counts) * T
+            buf = torch.full((len(counts) * m,), -1, dtype=torch.int64)
+            for g, c in enumerate(counts):
+                buf[g * m: g * m + c * T] = g * 1000 + torch.arange(c * T)
+            for dst, src, n in sp["copies"]:
+                assert dst + n <= src or src + n <= dst                # moves never overlap
+                buf[dst:dst + n] = buf[src:src + n].clone()
+            want = sorted(g * 1000 + i for g, c in enumerate(counts) if g != r for i in range(c * T))
+            assert sorted(buf[: sp["remote_rows"]].tolist()) == want, (counts, r)
