@@ -70,7 +70,7 @@ int pi3b_attn_fwd_hd64_lse(void* stream, const void* q, const void* k, const voi
                            int num_seqs, int q_len, int kv_len, int num_heads, float scale);
 
 /* pi3b_attn_fwd_hd64 / _lse (lse may be NULL) with a caller-provided scratch buffer: workspace (device, 4-byte aligned,
- * >= 4 * num_seqs * num_heads bytes; NULL = none). With it, sequences longer than 8192 keys run the BOUNDED-REFERENCE
+ * >= 4 * num_seqs * num_heads bytes; NULL = none). With it, sequences longer than 3000 keys (the three-tile kernel) run the BOUNDED-REFERENCE
  * softmax: one streaming pass over K finds max |k|^2 per (sequence, head), |q| max|k| * scale bounds every score of a
  * row, and the softmax is evaluated against that fixed reference instead of tracking the running maximum (identical
  * mathematics, within rounding; rows whose bound would be looser than 2^100 stay on the online path). The workspace

@@ -18,13 +18,13 @@
 //     issue slots per element of a scalar polynomial; its accuracy (degree 2: 2^-9.2) is matched to the bf16 rounding
 //     of P (2^-9) that follows.
 //
-// attn_fwd_kernel_t3 (kv_len > 8192, the chunk-global layers): THREE Q tiles per CTA so that three softmax warps share
+// attn_fwd_kernel_t3 (kv_len > 3000: the chunk-global layers, MoGe's 3.6k-token encoder): THREE Q tiles per CTA so that three softmax warps share
 // each scheduler; S 3x64, O 3x64, P 3x32 TMEM columns (480 of 512); ONE ISSUER WARP PER TILE (with one issuer and grouped
 // waits the tiles ran in lockstep, their exponential phases coincided on the MUFU pipe: 645 vs 888 TFLOP/s,
 // profiles/r01_attn_rev8_ab.log); a softmax warp hands S back as soon as the scores are in registers (s_free) so QK(j+1)
 // runs under this step's exponentials; setmaxnreg 48/152 (budgets must add up to the launch allocation).
 //
-// attn_fwd_kernel_t4 (kv_len <= 8192, frame-local layers): FOUR Q tiles, P written in place over the first 32 columns
+// attn_fwd_kernel_t4 (kv_len <= 3000, frame-local layers): FOUR Q tiles, P written in place over the first 32 columns
 // of its own S tile (S/P 4x64 + O 4x64 = 512 columns), four softmax warps per scheduler, two issuer warps serving two
 // tiles each in a fixed order: PV(j) then QK(j+1) back to back (the in-order tensor pipe makes the new scores overwrite P
 // only after PV has read it). The softmax step is two passes over 32-column halves (row max, then exponentials, S re-read
@@ -335,7 +335,7 @@ __device__ __forceinline__ float q_row_sqnorm(uint32_t q_tile_saddr, int row) {
 }
 
 // =====================================================================================================================
-// Three-tile kernel (kv_len > 8192)
+// Three-tile kernel (long sequences)
 // =====================================================================================================================
 constexpr int kA3Threads = 512;
 constexpr int kA3Tiles = 3;
@@ -593,7 +593,7 @@ attn_fwd_kernel_t3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // =====================================================================================================================
-// Four-tile kernel (kv_len <= 8192)
+// Four-tile kernel (short sequences)
 // =====================================================================================================================
 constexpr int kA4Tiles = 4;
 constexpr int kA4Threads = 32 * (4 + 4 * kA4Tiles);   // warp 0 TMA, warps 1-2 issuers (2 tiles each), warps 4-19 softmax
@@ -859,6 +859,8 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const MergeParams p) {
 
 using namespace pi3b;
 
+constexpr int kLongSeqKeys = 3000;   // above: three-tile kernel with the bounded-reference softmax
+
 static int attn_launch(void* stream, const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                        int q_col0, int k_col0, int v_col0, void* out, int64_t ldo, float* lse, int num_seqs, int q_len,
                        int kv_len, int num_heads, float scale, void* workspace = nullptr, int64_t workspace_bytes = 0) {
@@ -871,15 +873,16 @@ static int attn_launch(void* stream, const void* q, const void* k, const void* v
   const uint64_t rows = uint64_t(num_seqs) * q_len;
   const uint64_t kv_rows = uint64_t(num_seqs) * kv_len;
   PI3B_REQUIRE(rows < (1ull << 31) && kv_rows < (1ull << 31), "pi3b_attn_fwd_hd64: too many rows");
-  // Dispatch by key/value length: the four-tile kernel for short sequences (frame-local attention, +9 % at S = 1004), the
-  // three-tile kernel for long ones (chunk-global attention, +1.5 % at S = 100400); same-box A/B in
-  // profiles/r01_attn_rev8_ab.log. PI3B_ATTN_TILES=3|4 forces one kernel (A/B runs and the both-kernels parity tests).
+  // Dispatch by key/value length, from a same-box sweep at constant work (profiles/r02_attn_dispatch_threshold.json, ms for
+  // three-tile + bounded reference / four-tile): S=1004 0.635 / 0.591, 2048 0.504 / 0.502, 3571 0.462 / 0.519, 4096 0.445 /
+  // 0.503, 8192 0.545 / 0.636, 64300 17.2 / 19.0 — the four-tile kernel for the frame-local layers (T ~ 1k), the
+  // three-tile kernel from ~3k keys up. PI3B_ATTN_TILES=3|4 forces one kernel (A/B runs and the both-kernels parity tests).
   static const int forced = []() {
     const char* e = getenv("PI3B_ATTN_TILES");
     const int r = e ? atoi(e) : 0;
     return (r == 3 || r == 4) ? r : 0;
   }();
-  const int tiles = forced ? forced : (kv_len <= 8192 ? 4 : 3);
+  const int tiles = forced ? forced : (kv_len <= kLongSeqKeys ? 4 : 3);
   const int rows_per_cta = 128 * tiles;
 
   AttnParams p;

@@ -13,10 +13,10 @@ def _ref(qkv, B, S, H):
 
 # (num_seqs, seq_len, heads): frame-local shapes (T=261, 643, 1004), multiples of the tile sizes, ragged
 # tails on both the Q and the KV side, and a chunk-global shape.
-# Sequences up to 8192 keys run the four-tile kernel, longer ones the three-tile kernel: both sides of the dispatch are
+# Sequences up to 3000 keys run the four-tile kernel, longer ones the three-tile kernel: both sides of the dispatch are
 # covered, and test_each_kernel_when_forced pins each kernel on both kinds of shape.
 CASES = [(1, 128, 1), (1, 256, 2), (2, 384, 2), (3, 261, 16), (2, 643, 4), (2, 1004, 16), (1, 5, 1), (1, 129, 2),
-         (1, 8 * 261, 16), (1, 4099, 3), (1, 9001, 2), (1, 8193, 1)]
+         (1, 8 * 261, 16), (1, 3000, 2), (1, 3001, 2), (1, 4099, 3), (1, 9001, 2), (1, 8193, 1)]
 
 
 @pytest.mark.parametrize("B,S,H", CASES)
@@ -136,7 +136,7 @@ def test_lse_and_merge_over_key_blocks(S, H, splits):
 
 @pytest.mark.parametrize("outlier", [0.0, 60.0])
 def test_bounded_reference_softmax_and_its_fallback(outlier):
-    """Sequences longer than 8192 keys run the bounded-reference softmax (reference = |q| max|k| scale instead of the
+    """Sequences longer than 3000 keys run the bounded-reference softmax (reference = |q| max|k| scale instead of the
     running maximum). outlier = 0: the bound is tight enough and the fixed reference is adopted. outlier = 60: one key
     with a 60x larger norm makes the Cauchy-Schwarz bound ~500 (log2 units) above the typical scores, so the warps must
     stay on the online path — both against an fp64 softmax on sampled rows."""
