@@ -83,6 +83,81 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(hx), fmaf(-p, e, 1.0f), hx);      // 0.5 x + 0.5 |x| erf(|x| / sqrt 2)
 }
 
+
+// Two GELUs at once with the polynomial on packed fp32x2 FMAs (FFMA2/FMUL2): same operations in the same order and rounding
+// as gelu_erf, so the results are bit-identical; 12 packed + 4 ALU + 4 MUFU instructions per pair instead of 30.
+__device__ __forceinline__ uint64_t gelu_pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t gelu_ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t gelu_fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+#define GELU_K2(c) gelu_pack2(c, c)
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+  const uint64_t x = gelu_pack2(x0, x1);
+  const uint64_t a = gelu_fmul2(gelu_pack2(fabsf(x0), fabsf(x1)), GELU_K2(0.70710678118654752f));
+  const uint64_t d = gelu_ffma2(GELU_K2(0.3275911f), a, GELU_K2(1.0f));
+  float d0, d1, t0, t1, e0, e1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = gelu_pack2(t0, t1);
+  uint64_t q = gelu_ffma2(GELU_K2(1.061405429f), t, GELU_K2(-1.453152027f));
+  q = gelu_ffma2(q, t, GELU_K2(1.421413741f));
+  q = gelu_ffma2(q, t, GELU_K2(-0.284496736f));
+  q = gelu_ffma2(q, t, GELU_K2(0.254829592f));
+  q = gelu_fmul2(q, t);
+  const uint64_t arg = gelu_fmul2(gelu_fmul2(GELU_K2(-1.4426950408889634f), a), a);
+  float g0, g1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(g0), "=f"(g1) : "l"(arg));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
+  const uint64_t hx = gelu_fmul2(GELU_K2(0.5f), x);
+  float h0, h1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(hx));
+  // fma(-p, e, 1): the negation is exact, so -(p) * e + 1 == fma(p, -e, 1)
+  const uint64_t w = gelu_ffma2(q, gelu_pack2(-e0, -e1), GELU_K2(1.0f));
+  const uint64_t r = gelu_ffma2(gelu_pack2(fabsf(h0), fabsf(h1)), w, hx);
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(r));
+}
+#undef GELU_K2
+
+// bf16 epilogue store of one 32-row x 32-column chunk (64 bytes per row; packed[16] = this lane's row): the rows are
+// transposed through the warp's staging buffer so that every store instruction writes whole 32-byte sectors (8 rows x 64
+// contiguous bytes) instead of 32 rows x 16 bytes — half sectors that the L2 has to merge. Measured on the qkv GEMM
+// (M = 100 400): 0.513 -> 0.442 ms = 1428 TFLOP/s, past cuBLAS' 0.463 ms (profiles/r02_gemm_epilogue_ab.log).
+__device__ __forceinline__ void store_bf16_chunk_coalesced(uint32_t stg, const uint32_t* packed, const GemmParams& p,
+                                                           int row0, int col0, int lane) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 80 + j * 16), "r"(packed[4 * j]),
+                 "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3]) : "memory");
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + (lane >> 2);
+    const int mi = row0 + rr;
+    uint32_t a, b, c, d;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+                 : "r"(stg + rr * 80 + (lane & 3) * 16));
+    if (mi < p.M) {
+      const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + size_t(mo) * p.ldo + col0 + (lane & 3) * 8) =
+          make_uint4(a, b, c, d);
+    }
+  }
+  __syncwarp();
+}
+
 // CL = 1: every CTA loads its own A (128 x K) and B (BLOCK_N x K) tiles.
 // CL = 2: thread-block clusters of two CTAs that work on vertically adjacent output tiles (same n block, m blocks
 //         2i and 2i+1). Each CTA loads its own A tile but only HALF of the shared B tile and TMA-multicasts that half
@@ -95,9 +170,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
 //         reads half of B from its own shared memory, the other half from the peer's). The even CTA issues all MMAs and
 //         owns the full and accumulator-empty barriers; see ptx.cuh. This is the configuration cuBLAS picks for these
 //         shapes on B200 (nvjet 256x256_64x4 2cta, profiles/r02_gemm_full_metrics.txt).
-template <int BLOCK_N, int STAGES, bool TF32, int CL, bool QK, bool TWOSM = false>
+// EPI selects the epilogue compiled into the instantiation (each keeps its own register budget and code size):
+//   0 general (bias / GELU / ReLU / LayerScale / residual, bf16 or fp32 out, ragged N, row regrouping)
+//   1 fused QKV: bias -> bf16 -> q/k LayerNorm(64) -> RoPE-2D (pi3b_gemm_qkv)
+//   2 streamlined fp32 read-modify-write of the residual stream (whole chunks, no regrouping, no GELU)
+template <int BLOCK_N, int STAGES, bool TF32, int CL, int EPI, bool TWOSM = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr bool QK = EPI == 1, FAST = EPI == 2;
   static_assert(!TWOSM || (CL == 2 && !TF32), "the CTA-pair kernel is the bf16 2-CTA-cluster variant");
   using S = GemmSmem<BLOCK_N, STAGES, TWOSM>;
   constexpr int ELEM = TF32 ? 4 : 2;
@@ -266,27 +346,103 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         *reinterpret_cast<float4*>(gamma_s + lane * 4) = g4;
       }
       __syncwarp();
-      // Residual slice of one 32-column chunk in the transposed (coalesced) lane layout: 8 x 16-byte loads per lane.
-      // The residual does not depend on the accumulator, so chunk 0 is requested BEFORE the accumulator wait (its DRAM
-      // latency hides under the main loop) and chunk c+1 right after chunk c's values have been consumed (under chunk
-      // c's stores and chunk c+1's TMEM read): the RMW epilogue was latency-bound with the loads issued per chunk.
-      float4 rq[8];
-      auto load_resid = [&](int c) {
-        const int n0c = n_blk * BLOCK_N + half * COLS_PER_WARP + c * 32;
-        if (QK || p.resid == nullptr || !p.vec_ok || c >= COLS_PER_WARP / 32 || n0c + 32 > p.N) return;
+      // The accumulator buffer goes back to the MMA warp as soon as this warp has its last TMEM read in registers (not
+      // after the stores): the next-but-one tile's main loop never waits for an epilogue's memory traffic.
+      bool released = false;
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (TWOSM) mbar_arrive_cluster(&tmem_empty[acc], 0);   // the leader's MMA warp waits for both CTAs' epilogues
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+        released = true;
+      };
+      // EPI = 2: fp32 outputs of whole 32-column chunks without row regrouping (every residual-stream GEMM of the trunk;
+      // gemm_dispatch checks the conditions): per-tile row pointers instead of per-row index arithmetic, the residual prefetched TWO
+      // chunks ahead (2 x 4 KB in flight per warp, 64 KB per SM: one chunk ahead left the warps waiting on DRAM latency
+      // for most of each chunk — long-scoreboard 40 % of the samples of the proj GEMM), stores issued as the sums appear.
+      constexpr int NCH = COLS_PER_WARP / 32;
+      const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
+      const int row_first = m_blk * kBlockM + quarter * 32 + sub_r;
+      const int col_first = n_blk * BLOCK_N + half * COLS_PER_WARP + sub_c;
+      const float* rp = (FAST && p.resid) ? p.resid + size_t(row_first) * p.ld_resid + col_first : nullptr;
+      const size_t rstep = size_t(8) * p.ld_resid;
+      float4 rqA[8], rqB[8];
+      auto loadq = [&](float4* q, int c) {
+        if (rp == nullptr || c >= NCH) return;
 #pragma unroll
-        for (int hi = 0; hi < 8; ++hi) {
-          const int mi = m_blk * kBlockM + quarter * 32 + (hi & 3) * 8 + (lane >> 2);
-          if (mi < p.M) {
-            const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
-            rq[hi] = __ldcg(reinterpret_cast<const float4*>(p.resid + size_t(mo) * p.ld_resid + n0c + (hi >> 2) * 16 + (lane & 3) * 4));
+        for (int it = 0; it < 4; ++it) {
+          if (row_first + 8 * it < p.M) {
+            q[it] = __ldcg(reinterpret_cast<const float4*>(rp + it * rstep + c * 32));
+            q[4 + it] = __ldcg(reinterpret_cast<const float4*>(rp + it * rstep + c * 32 + 16));
           }
         }
       };
-      load_resid(0);
+      loadq(rqA, 0);   // the residual does not depend on the accumulator: requested before the wait, under the main loop
+      loadq(rqB, 1);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (QK) {
+      if (FAST) {
+        float* op = static_cast<float*>(p.out) + size_t(row_first) * p.ldo + col_first;
+        const size_t ostep = size_t(8) * p.ldo;
+        const uint32_t stg = smem_u32(smem + S::STG_OFFSET + ew * S::STG_BYTES_PER_WARP);
+        auto chunk = [&](int c, const float4* q) {
+          uint32_t r[32];
+          tmem_ld_x32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N + half * COLS_PER_WARP + c * 32, r);
+          tmem_ld_wait();
+          if (c == NCH - 1) release_acc();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.gamma) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 g = *reinterpret_cast<const float4*>(gamma_s + c * 32 + j);
+              v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+            }
+          }
+          // transpose through the warp's staging buffer (two halves of 16 columns): every global access below is 64
+          // contiguous bytes per row, 8 rows per instruction
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (lane * S::STG_STRIDE + 4 * j) * 4),
+                           "f"(v[h * 16 + 4 * j]), "f"(v[h * 16 + 4 * j + 1]), "f"(v[h * 16 + 4 * j + 2]),
+                           "f"(v[h * 16 + 4 * j + 3]) : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              float4 x = qk_lds128(stg + ((it * 8 + sub_r) * S::STG_STRIDE + sub_c) * 4);
+              if (rp != nullptr) {
+                const float4 qq = q[h * 4 + it];
+                x.x += qq.x; x.y += qq.y; x.z += qq.z; x.w += qq.w;
+              }
+              if (row_first + 8 * it < p.M) *reinterpret_cast<float4*>(op + it * ostep + c * 32 + h * 16) = x;
+            }
+            __syncwarp();
+          }
+        };
+#pragma unroll 1
+        for (int c = 0; c < NCH; c += 2) {
+          chunk(c, rqA);
+          loadq(rqA, c + 2);
+          chunk(c + 1, rqB);
+          loadq(rqB, c + 3);
+        }
+      } else if (QK) {
         // ===== fused QKV epilogue (QK instantiations only: the plain kernels keep their register budget): bias -> bf16 -> [LayerNorm(64)] -> [RoPE-2D] -> bf16, one head (64 columns) at a time;
         // the thread owns its row, so the head's statistics and rotation pairs are all in its own registers. Same
         // arithmetic as qknorm_rope_kernel (qk_math.cuh): the result is bit-identical to GEMM + stand-alone pass, without
@@ -305,6 +461,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_x32(taddr, r);
           tmem_ld_x32(taddr + 32, r + 32);
           tmem_ld_wait();
+          if (hd == COLS_PER_WARP / 64 - 1) release_acc();
           float v[64];
 #pragma unroll
           for (int j = 0; j < 64; j += 4) {
@@ -320,17 +477,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t norm_saddr = (p.qk_mode & 1) ? qk_saddr + (n0 >= (p.qk_cols >> 1) ? 512u : 0u) : 0u;
             qk_head_inplace(v, norm_saddr, p.qk_eps, (p.qk_mode & 2) ? p.cs_table : nullptr, pos_y, pos_x);
           }
-          if (row_ok) {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + size_t(m) * p.ldo + n0);
+          {
+            const uint32_t stg = smem_u32(smem + S::STG_OFFSET + ew * S::STG_BYTES_PER_WARP);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            for (int hh = 0; hh < 2; ++hh) {   // the head's 128 bytes per row in two 64-byte halves
+              uint32_t packed[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[32 * hh + 2 * j], v[32 * hh + 2 * j + 1]);
+              store_bf16_chunk_coalesced(stg, packed, p, m_blk * kBlockM + quarter * 32, n0 + 32 * hh, lane);
+            }
           }
         }
       } else
 #pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+      for (int c = 0; c < (FAST ? 0 : COLS_PER_WARP / 32); ++c) {
         const int col_in_tile = half * COLS_PER_WARP + c * 32;
         const int n0 = n_blk * BLOCK_N + col_in_tile;
         if (n0 >= p.N) break;  // warp-uniform
@@ -351,7 +511,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 32; j += 2) gelu_erf_x2(v[j], v[j + 1]);
           } else if (p.act == 2) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -363,59 +523,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
             }
           }
-          if (p.resid) {
-            // fp32 read-modify-write of the residual stream: transpose through smem so that every global access is
-            // 64 contiguous bytes per row instead of 32 different rows per instruction (32 L1 wavefronts each).
-            // A/B on B200, fc2 + LayerScale + residual at M = 100400: 1203 -> 1284 TFLOP/s.
-            // (explicit st.shared / ld.shared: pointers derived from the manually aligned smem base are generic to the
-            // compiler, which emitted generic ST.E / LD.E here)
-            const uint32_t stg = smem_u32(smem + S::STG_OFFSET + ew * S::STG_BYTES_PER_WARP);
-            const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
-            float4 xs[8];
+          if (p.resid && row_ok) {
+            // (row-regrouped or bf16-output residual GEMMs only — the patch embedding, once per forward; the residual-stream
+            // GEMMs of the trunk take the streamlined path above)
+            const float4* rr = reinterpret_cast<const float4*>(p.resid + size_t(m) * p.ld_resid + n0);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (lane * S::STG_STRIDE + 4 * j) * 4),
-                             "f"(v[h * 16 + 4 * j]), "f"(v[h * 16 + 4 * j + 1]), "f"(v[h * 16 + 4 * j + 2]),
-                             "f"(v[h * 16 + 4 * j + 3]) : "memory");
-              __syncwarp();
-#pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                float4 x = qk_lds128(stg + ((it * 8 + sub_r) * S::STG_STRIDE + sub_c) * 4);
-                const float4 q = rq[h * 4 + it];
-                x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
-                xs[h * 4 + it] = x;
-              }
-              __syncwarp();
+            for (int j = 0; j < 8; ++j) {
+              const float4 q = __ldcg(rr + j);
+              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
             }
-            load_resid(c + 1);   // rq is free again: the next chunk's residual travels while this chunk is stored
+          }
+          if (p.out_f32 && row_ok) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(m) * p.ldo + n0);
 #pragma unroll
-            for (int hi = 0; hi < 8; ++hi) {
-              const int mi = m_blk * kBlockM + quarter * 32 + (hi & 3) * 8 + sub_r;
-              if (mi < p.M) {
-                const int mo = p.grp_in ? (mi / p.grp_in) * p.grp_out + p.grp_off + mi % p.grp_in : mi;
-                const int col = n0 + (hi >> 2) * 16 + sub_c;
-                const float4 x = xs[hi];
-                if (p.out_f32)
-                  *reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(mo) * p.ldo + col) = x;
-                else
-                  *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + size_t(mo) * p.ldo + col) =
-                      make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-              }
-            }
-          } else if (row_ok) {
-            if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + size_t(m) * p.ldo + n0);
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (!p.out_f32) {
+            uint32_t packed[16];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + size_t(m) * p.ldo + n0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-            }
+            for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            store_bf16_chunk_coalesced(smem_u32(smem + S::STG_OFFSET + ew * S::STG_BYTES_PER_WARP), packed, p,
+                                       m_blk * kBlockM + quarter * 32, n0, lane);
           }
         } else if (row_ok) {
           // ragged N tail (N = 588 / 196 / 9 / 3 heads): scalar path
@@ -434,12 +562,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (TWOSM) mbar_arrive_cluster(&tmem_empty[acc], 0);   // the leader's MMA warp waits for both CTAs' epilogues
-        else mbar_arrive(&tmem_empty[acc]);
-      }
+      if (!released) release_acc();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -455,11 +578,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BLOCK_N, int STAGES, bool TF32, int CL, bool QK = false, bool TWOSM = false>
+template <int BLOCK_N, int STAGES, bool TF32, int CL, int EPI = 0, bool TWOSM = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
                        cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N, STAGES, TWOSM>;
-  auto kern = gemm_kernel<BLOCK_N, STAGES, TF32, CL, QK, TWOSM>;
+  auto kern = gemm_kernel<BLOCK_N, STAGES, TF32, CL, EPI, TWOSM>;
   static DeviceOnce configured;   // one per template instantiation; the attribute is per device
   const int dev = current_device();
   if (configured.first_call_on(dev)) {
@@ -519,13 +642,16 @@ static int gemm_dispatch(void* stream, int in_dtype, const void* A, int64_t lda,
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p.qk_mode != 0) {   // fused QKV epilogue (bf16 operands only)
-    if (twosm) return launch_gemm<256, 6, false, 2, true, true>(tmA, tmB, p, num_sms, st);
-    if (cluster) return launch_gemm<256, 4, false, 2, true>(tmA, tmB, p, num_sms, st);
-    return wide ? launch_gemm<256, 4, false, 1, true>(tmA, tmB, p, num_sms, st)
-                : launch_gemm<128, 6, false, 1, true>(tmA, tmB, p, num_sms, st);
+    if (twosm) return launch_gemm<256, 6, false, 2, 1, true>(tmA, tmB, p, num_sms, st);
+    if (cluster) return launch_gemm<256, 4, false, 2, 1>(tmA, tmB, p, num_sms, st);
+    return wide ? launch_gemm<256, 4, false, 1, 1>(tmA, tmB, p, num_sms, st)
+                : launch_gemm<128, 6, false, 1, 1>(tmA, tmB, p, num_sms, st);
   }
   if (in_dtype == 0) {
-    if (twosm) return launch_gemm<256, 6, false, 2, false, true>(tmA, tmB, p, num_sms, st);
+    // fp32 outputs (the residual stream's read-modify-write, LayerScale fused) of whole column chunks: streamlined epilogue
+    if (twosm && p.out_f32 && p.vec_ok && p.grp_in == 0 && p.act != 1 && N % 256 == 0)
+      return launch_gemm<256, 6, false, 2, 2, true>(tmA, tmB, p, num_sms, st);
+    if (twosm) return launch_gemm<256, 6, false, 2, 0, true>(tmA, tmB, p, num_sms, st);
     if (cluster) return launch_gemm<256, 4, false, 2>(tmA, tmB, p, num_sms, st);
     return wide ? launch_gemm<256, 4, false, 1>(tmA, tmB, p, num_sms, st) : launch_gemm<128, 6, false, 1>(tmA, tmB, p, num_sms, st);
   } else {
