@@ -43,13 +43,15 @@ int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda, const void
  * (A[M,K] * W[3*64*num_heads, K]^T + bias) rounded to bf16, then on every 64-channel head of the q and k thirds
  * LayerNorm(64) (qk_norm = fp32 [4][64]: q weight, q bias, k weight, k bias; NULL to skip) and 2-D RoPE (cs_table fp32
  * [table_rows][16][2] = (cos, sin) of pos * base^(-j/16); NULL to skip; token geometry as pi3b_qknorm_rope); the v third
- * is stored as is. Bit-identical to pi3b_gemm followed by pi3b_qknorm_rope, without that pass's read-modify-write of the
+ * is stored as is. q_scale (1 = none): the query heads are multiplied by it before their final rounding to bf16 — pass
+ * softmax_scale * log2(e) and call the attention with scale = ln 2: the long-sequence kernel then feeds its accumulator
+ * straight to exp2 ("zero-reference" softmax, no scale-and-subtract per score). Bit-identical to pi3b_gemm followed by pi3b_qknorm_rope, without that pass's read-modify-write of the
  * q and k thirds (822 MB per layer at 100 400 tokens). A, W bf16.
  * replaces: qkv Linear + q_norm / k_norm + rope of pi3/models/layers/attention.py:326-334 in one launch; supersedes the
  *   reference's native rope_2d_cuda_kernel (pi3/models/curope/kernels.cu:17-108), which is a separate in-place pass. */
 int pi3b_gemm_qkv(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int num_heads, int K,
                   const float* bias, void* out, int64_t ldo, const float* qk_norm, float eps, const float* cs_table,
-                  int table_rows, int tokens_per_frame, int n_special, int patch_w);
+                  int table_rows, int tokens_per_frame, int n_special, int patch_w, float q_scale);
 
 /* out = softmax(q k^T * scale) v, head_dim 64, bf16, per (sequence, head). Sequence s owns query / output rows
  * [s*q_len, (s+1)*q_len) and key / value rows [s*kv_len, (s+1)*kv_len) (q_len != kv_len: the sequence-parallel case,
@@ -102,13 +104,13 @@ int pi3b_layernorm(void* stream, const float* x, int64_t ldx, const float* gamma
 /* In place on the q and k thirds of packed qkv [M, 3*64*heads] bf16: optional LayerNorm(64) (q/k-norm params
  * fp32 [64], all four NULL to skip) then 2-D RoPE (do_rope) with cs_table fp32 [table_rows][16][2] = (cos, sin) of
  * pos * base^(-j/16). Token t = row % tokens_per_frame; t < n_special => position (0,0) (identity);
- * otherwise (y, x) = ((t-n_special) / patch_w + 1, (t-n_special) % patch_w + 1).
+ * otherwise (y, x) = ((t-n_special) / patch_w + 1, (t-n_special) % patch_w + 1). q_scale as in pi3b_gemm_qkv.
  * replaces: q_norm/k_norm + rope of pi3/models/layers/attention.py:330-334, RoPE2D pi3/models/layers/pos_embed.py:112-159,
  *   PositionGetter :162-174, and the reference's only native kernel rope_2d_cuda_kernel pi3/models/curope/kernels.cu:17-108
  *   (pybind rope_2d, pi3/models/curope/curope.cpp:49-69). */
 int pi3b_qknorm_rope(void* stream, void* qkv, int64_t ld, int M, int num_heads, int tokens_per_frame, int n_special,
                      int patch_w, const float* qn_w, const float* qn_b, const float* kn_w, const float* kn_b, float eps,
-                     const float* cs_table, int table_rows, int do_rope);
+                     const float* cs_table, int table_rows, int do_rope, float q_scale);
 
 /* imgs fp32 [N,3,H,W] in [0,1] -> out bf16 [N*(H/14)*(W/14), ldk]: normalised ((x-mean)/std) im2col of the 14x14/s14
  * patch conv, column c*196 + 14*i + j, columns [588, ldk) zero. mean3/std3: HOST pointers to 3 floats.

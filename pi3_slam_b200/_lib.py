@@ -23,9 +23,10 @@ SIGNATURES = {
     # stream, in_dtype, A, lda, W, ldw, M, N, K, bias, gamma, resid, ld_resid, out, ldo, out_f32, act, grp_in, grp_out, grp_off
     "pi3b_gemm": (c_int, [_P, c_int, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, _P,
                           c_int64, c_int, c_int, c_int, c_int, c_int]),
-    # stream, A, lda, W, ldw, M, num_heads, K, bias, out, ldo, qk_norm, eps, cs_table, table_rows, tokens_per_frame, n_special, patch_w
+    # stream, A, lda, W, ldw, M, num_heads, K, bias, out, ldo, qk_norm, eps, cs_table, table_rows, tokens_per_frame, n_special,
+    # patch_w, q_scale
     "pi3b_gemm_qkv": (c_int, [_P, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, c_int64, _P, c_float, _P, c_int,
-                              c_int, c_int, c_int]),
+                              c_int, c_int, c_int, c_float]),
     # stream, q, k, v, ldq, ldk, ldv, q_col0, k_col0, v_col0, out, ldo, num_seqs, q_len, kv_len, num_heads, scale
     "pi3b_attn_fwd_hd64": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64,
                                    c_int, c_int, c_int, c_int, c_float]),
@@ -39,9 +40,10 @@ SIGNATURES = {
     "pi3b_attn_merge": (c_int, [_P, c_int, _P, _P, c_int64, _P, c_int64, _P, c_int, c_int]),
     # stream, x, ldx, gamma, beta, eps, out, ldo, out_f32, M, D, override_rows, period, n_override
     "pi3b_layernorm": (c_int, [_P, _P, c_int64, _P, _P, c_float, _P, c_int64, c_int, c_int, c_int, _P, c_int, c_int]),
-    # stream, qkv, ld, M, heads, tokens_per_frame, n_special, patch_w, qn_w, qn_b, kn_w, kn_b, eps, cs_table, table_rows, do_rope
+    # stream, qkv, ld, M, heads, tokens_per_frame, n_special, patch_w, qn_w, qn_b, kn_w, kn_b, eps, cs_table, table_rows, do_rope,
+    # q_scale
     "pi3b_qknorm_rope": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_float, _P,
-                                 c_int, c_int]),
+                                 c_int, c_int, c_float]),
     # stream, imgs, out, N, H, W, ldk, mean3(host), std3(host)
     "pi3b_patch_pack": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     # stream, table, out, num_groups, rows_per_group, D

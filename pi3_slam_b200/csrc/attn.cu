@@ -64,6 +64,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   int ldo;
   float scale_log2;  // softmax scale * log2(e)
+  int unit_scale;    // scale_log2 == 1 exactly: q was pre-multiplied by scale * log2(e) (pi3b_gemm_qkv's q_scale)
   float* lse;        // optional fp32 [num_heads][num_seqs * q_len]: max + log2(sum) of the scaled log2-domain scores
   // optional fp32 [num_seqs][num_heads]: max over the sequence's keys of |k|^2 (kmax2_kernel). Enables the bounded-
   // reference softmax of the three-tile kernel: |q . k| <= |q| max|k| is an a-priori upper bound of every score of a row
@@ -150,11 +151,13 @@ __device__ __forceinline__ void poly_exp2_x2(uint64_t x, float& p0, float& p1) {
 
 // exponentials of NCOL scores held in registers: a[c] (fp32 bit patterns) -> packed bf16 P in out[0 .. NCOL/2), row sum
 // accumulated in the packed pair `lsum`. x = score * scale_log2 - m_used.
-template <int NCOL>
+// RAW = true: the scores are already in their final units (log2 domain, reference 0): no scale-and-subtract at all.
+template <int NCOL, bool RAW = false>
 __device__ __forceinline__ void exp_block(const uint32_t* a, uint32_t* out, uint64_t sc2, uint64_t negm2, uint64_t& lsum) {
 #pragma unroll
   for (int c = 0; c < NCOL; c += 2) {
-    const uint64_t x = ffma2(pack2(__uint_as_float(a[c]), __uint_as_float(a[c + 1])), sc2, negm2);
+    const uint64_t xin = pack2(__uint_as_float(a[c]), __uint_as_float(a[c + 1]));
+    const uint64_t x = RAW ? xin : ffma2(xin, sc2, negm2);
     float p0, p1;
     // pairs are spread evenly over the row so that ptxas can interleave the FMA-pipe chains with the MUFU stream
     const bool poly = (((c >> 1) % 8) * PI3B_POLY_PAIRS) % 8 < PI3B_POLY_PAIRS;
@@ -527,8 +530,9 @@ attn_fwd_kernel_t3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (lane == 0) mbar_arrive(&p_full[t]);
       };
       // The same step with a FIXED reference m_used (bounded-reference softmax, see above): no row maximum, no rescale vote.
-      auto step_fixed = [&](const int j, const uint64_t negm2, auto mask_tag) {
+      auto step_fixed = [&](const int j, const uint64_t negm2, auto mask_tag, auto raw_tag) {
         constexpr bool MASK = decltype(mask_tag)::value;
+        constexpr bool RAW = decltype(raw_tag)::value;
         if (!s_ready) mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
         uint32_t sr[64];
@@ -541,7 +545,7 @@ attn_fwd_kernel_t3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (MASK) mask_tail<64>(sr, 0, p.kv_len - j * 64);
         // (moving the two polls into the middle of the exponentials measured no gain: profiles/r02_attn_poly_ab.log "mid2")
         const bool pv_ready = mbar_try_wait(&pv_done[t], (j - 1) & 1);
-        exp_block<64>(sr, sr, sc2, negm2, lsum);
+        exp_block<64, RAW>(sr, sr, sc2, negm2, lsum);
         s_ready = !MASK && mbar_try_wait(&s_full[t], (j + 1) & 1);
         if (!pv_ready) mbar_wait(&pv_done[t], (j - 1) & 1);
         tc_fence_after();
@@ -554,7 +558,7 @@ attn_fwd_kernel_t3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
       // loop bounds are compared against p.kv_len (constant bank) so that no register is held for the trip count
       int j = 0;
-      bool fixed = false;
+      bool fixed = false, zero = false;
       if (p.kmax2 != nullptr && p.kv_len > 64) {
         // a-priori bound of this row's scores (log2 domain), with a margin for the fp32 rounding of norms and products
         mbar_wait(q_full, 0);
@@ -563,16 +567,24 @@ attn_fwd_kernel_t3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         step(0, FalseTag{});                        // online first step: m_used = maximum of the first 64 scores <= true maximum
         j = 1;
         fixed = __all_sync(0xffffffffu, m_ref - m_used <= 100.0f);
-        if (fixed) {                                // move the reference up to the bound: O(0) and the row sum are rescaled once
+        // Unit scale (the caller folded scale * log2(e) into q: p.scale_log2 == 1) and every score of the warp's rows
+        // within [-100, 100] of zero: zero itself is a valid reference — exp2 is applied to the accumulator as it comes
+        // out of TMEM, the scale-and-subtract FFMA2 per pair of scores disappears (64 of ~450 instructions per step).
+        // 2^100 x 100 400 keys stays far inside fp32 and bf16 range; m_used >= -100 keeps the dominant terms >= 2^-100.
+        zero = p.unit_scale && __all_sync(0xffffffffu, m_ref <= 100.0f && m_used >= -100.0f);
+        if (fixed || zero) {                        // move the reference (up to the bound, or to zero): O(0) and the row sum are rescaled once
           mbar_wait(&pv_done[t], 0);
           tc_fence_after();
-          rescale_row(true, m_ref, m_used, lsum, tm_o);
+          rescale_row(true, zero ? 0.0f : m_ref, m_used, lsum, tm_o);
         }
       }
-      if (fixed) {
+      if (zero) {
+        for (; (j + 1) * 64 < p.kv_len; ++j) step_fixed(j, 0ull, FalseTag{}, TrueTag{});
+        step_fixed(j, 0ull, TrueTag{}, TrueTag{});
+      } else if (fixed) {
         const uint64_t negm2 = pack2(-m_used, -m_used);
-        for (; (j + 1) * 64 < p.kv_len; ++j) step_fixed(j, negm2, FalseTag{});
-        step_fixed(j, negm2, TrueTag{});
+        for (; (j + 1) * 64 < p.kv_len; ++j) step_fixed(j, negm2, FalseTag{}, FalseTag{});
+        step_fixed(j, negm2, TrueTag{}, FalseTag{});
       } else {
         for (; (j + 1) * 64 < p.kv_len; ++j) step(j, FalseTag{});
         step(j, TrueTag{});   // last step: columns past kv_len (if any) are masked to -inf
@@ -891,6 +903,10 @@ static int attn_launch(void* stream, const void* q, const void* k, const void* v
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = (int)ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
+  // scale = ln 2 announces queries that already carry scale * log2(e) (the fused QKV epilogue's q_scale)
+  static const bool zero_ok = []() { const char* e = getenv("PI3B_ATTN_ZEROREF"); return !(e && e[0] == '0'); }();
+  p.unit_scale = zero_ok && fabsf(p.scale_log2 - 1.0f) < 1e-6f;
+  if (p.unit_scale) p.scale_log2 = 1.0f;
   p.lse = lse;
   p.kmax2 = nullptr;
 

@@ -39,6 +39,7 @@ struct GemmParams {
   const float* qk_norm;
   const float2* cs_table;
   float qk_eps;
+  float q_scale;   // queries (columns [0, qk_cols / 2)) are multiplied by this before the final rounding (1 = none)
   int tokens_per_frame, n_special, patch_w;
 };
 
@@ -476,6 +477,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (n0 < p.qk_cols) {
             const uint32_t norm_saddr = (p.qk_mode & 1) ? qk_saddr + (n0 >= (p.qk_cols >> 1) ? 512u : 0u) : 0u;
             qk_head_inplace(v, norm_saddr, p.qk_eps, (p.qk_mode & 2) ? p.cs_table : nullptr, pos_y, pos_x);
+            if (p.q_scale != 1.0f && n0 < (p.qk_cols >> 1)) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) v[j] = qk_scale_out(v[j], p.q_scale);
+            }
           }
           {
             const uint32_t stg = smem_u32(smem + S::STG_OFFSET + ew * S::STG_BYTES_PER_WARP);
@@ -688,8 +693,10 @@ extern "C" int pi3b_gemm(void* stream, int in_dtype, const void* A, int64_t lda,
 
 extern "C" int pi3b_gemm_qkv(void* stream, const void* A, int64_t lda, const void* W, int64_t ldw, int M, int num_heads,
                              int K, const float* bias, void* out, int64_t ldo, const float* qk_norm, float eps,
-                             const float* cs_table, int table_rows, int tokens_per_frame, int n_special, int patch_w) {
+                             const float* cs_table, int table_rows, int tokens_per_frame, int n_special, int patch_w,
+                             float q_scale) {
   PI3B_REQUIRE(A && W && out, "pi3b_gemm_qkv: null pointer");
+  PI3B_REQUIRE(q_scale > 0.f, "pi3b_gemm_qkv: q_scale must be positive (1 = none)");
   PI3B_REQUIRE(M > 0 && num_heads > 0 && K > 0, "pi3b_gemm_qkv: bad shape");
   PI3B_REQUIRE(qk_norm || cs_table, "pi3b_gemm_qkv: neither q/k norm nor RoPE requested (use pi3b_gemm)");
   const int N = 3 * 64 * num_heads;
@@ -712,6 +719,7 @@ extern "C" int pi3b_gemm_qkv(void* stream, const void* A, int64_t lda, const voi
   p.qk_norm = qk_norm;
   p.cs_table = reinterpret_cast<const float2*>(cs_table);
   p.qk_eps = eps;
+  p.q_scale = q_scale;
   p.tokens_per_frame = tokens_per_frame > 0 ? tokens_per_frame : 1;
   p.n_special = n_special;
   p.patch_w = patch_w > 0 ? patch_w : 1;

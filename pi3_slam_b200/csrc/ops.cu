@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(__nv_bfloat16* __restr
                                                           const float* __restrict__ qn_b,
                                                           const float* __restrict__ kn_w,
                                                           const float* __restrict__ kn_b, float eps,
-                                                          const float2* __restrict__ cs_table, int do_rope) {
+                                                          const float2* __restrict__ cs_table, int do_rope,
+                                                          float q_scale) {
   // 32-bit index math only: the first version spent most of its instructions in 64-bit divisions
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int sub = int(gid & 7u);
@@ -168,6 +169,10 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(__nv_bfloat16* __restr
                               : qk_rope_first(x[2 * i + 1], partner[2 * i + 1], c.z, c.w);
         }
       }
+    }
+    if (which == 0 && q_scale != 1.0f) {   // queries leave pre-multiplied (softmax scale folded in), rounded to bf16 once
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = qk_scale_out(x[i], q_scale);
     }
     if (ok) {
       uint4 o;
@@ -430,8 +435,10 @@ extern "C" int pi3b_layernorm(void* stream, const float* x, int64_t ldx, const f
 
 extern "C" int pi3b_qknorm_rope(void* stream, void* qkv, int64_t ld, int M, int num_heads, int tokens_per_frame,
                                 int n_special, int patch_w, const float* qn_w, const float* qn_b, const float* kn_w,
-                                const float* kn_b, float eps, const float* cs_table, int table_rows, int do_rope) {
+                                const float* kn_b, float eps, const float* cs_table, int table_rows, int do_rope,
+                                float q_scale) {
   PI3B_REQUIRE(qkv && M > 0 && num_heads > 0, "pi3b_qknorm_rope: bad args");
+  PI3B_REQUIRE(q_scale > 0.f, "pi3b_qknorm_rope: q_scale must be positive (1 = none)");
   PI3B_REQUIRE(ld % 8 == 0 && ld >= 3 * 64 * num_heads, "pi3b_qknorm_rope: bad ld");
   PI3B_REQUIRE((qn_w == nullptr) == (kn_w == nullptr) && (qn_w == nullptr) == (qn_b == nullptr) &&
                    (kn_w == nullptr) == (kn_b == nullptr), "pi3b_qknorm_rope: norm params must be all set or all null");
@@ -444,7 +451,7 @@ extern "C" int pi3b_qknorm_rope(void* stream, void* qkv, int64_t ld, int M, int 
   PI3B_REQUIRE(threads < (1ll << 31), "pi3b_qknorm_rope: too many rows");
   qknorm_rope_kernel<<<blocks_for(threads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<__nv_bfloat16*>(qkv), ld, M, num_heads, tokens_per_frame, n_special, patch_w, qn_w, qn_b, kn_w, kn_b,
-      eps, reinterpret_cast<const float2*>(cs_table), do_rope);
+      eps, reinterpret_cast<const float2*>(cs_table), do_rope, q_scale);
   return check_launch("qknorm_rope launch");
 }
 

@@ -8,7 +8,8 @@
 //   * variance = the same tree over fma(d, d, acc), d = x - mean; rstd = rsqrtf(var / 64 + eps);
 //   * y = fma((x - mean) * rstd, w, b), rounded to bf16 (the reference casts the normed q/k to bf16 before RoPE);
 //   * RoPE pair (a, b) = channels (j, j + 16) of a 32-channel half, angle pos * base^(-j/16):
-//     a' = fma(a, cos, -(b * sin)), b' = fma(b, cos, a * sin); pos = 0 (special tokens) is the identity.
+//     a' = fma(a, cos, -(b * sin)), b' = fma(b, cos, a * sin); pos = 0 (special tokens) is the identity;
+//   * queries only, optional: x q_scale (one fp32 multiply) before the final rounding to bf16.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -43,6 +44,10 @@ __device__ __forceinline__ float qk_norm1(float x, float mean, float rstd, float
 // (a, b) = (first, second) member of a rotation pair
 __device__ __forceinline__ float qk_rope_first(float a, float b, float c, float s) { return __fmaf_rn(a, c, -__fmul_rn(b, s)); }
 __device__ __forceinline__ float qk_rope_second(float a, float b, float c, float s) { return __fmaf_rn(b, c, __fmul_rn(a, s)); }
+
+// optional last step for the queries: multiply by q_scale (the softmax scale x log2(e) folded into q, so that the attention
+// kernel can feed its accumulator straight to exp2) before the one rounding to bf16
+__device__ __forceinline__ float qk_scale_out(float x, float s) { return __fmul_rn(x, s); }
 
 // 16-byte load from shared memory by 32-bit shared address (pointers derived from the manually aligned dynamic smem base
 // are generic to the compiler, which would emit slower generic loads)

@@ -12,6 +12,11 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+# Softmax scale folded into the queries: q leaves the QKV epilogue multiplied by (1/8) * log2(e) and the attention is
+# called with scale = ln 2, i.e. softmax_2(q' k) == softmax_e(q k / 8). The long-sequence kernel then takes the
+# exponent straight from the accumulator (attn.cu, "zero reference").
+Q_PRESCALE = 0.125 * 1.4426950408889634
+ATTN_SCALE_PRESCALED = 0.6931471805599453
 
 
 def device_guard(get_device):
@@ -108,10 +113,11 @@ def _attn_workspace(device: torch.device) -> torch.Tensor:
 
 def gemm_qkv(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor], num_heads: int,
              qk_norm: Optional[torch.Tensor], eps: float, cs_table: Optional[torch.Tensor], tokens_per_frame: int,
-             n_special: int, patch_w: int) -> torch.Tensor:
+             n_special: int, patch_w: int, q_scale: float = 1.0) -> torch.Tensor:
     """QKV projection with q/k LayerNorm(64) and RoPE-2D fused into the GEMM epilogue (bit-identical to `gemm` followed by
     `qknorm_rope`). a [M,K], w [3*64*heads, K] bf16; out [M, 3*64*heads] bf16; qk_norm fp32 [4,64] (q weight, q bias,
-    k weight, k bias) or None; cs_table fp32 [max_pos+1, 16, 2] or None."""
+    k weight, k bias) or None; cs_table fp32 [max_pos+1, 16, 2] or None. q_scale: the queries are multiplied by it
+    before their final rounding (`Q_PRESCALE` with attention `scale=ATTN_SCALE_PRESCALED`: the softmax scale rides on q)."""
     lib = _lib.load()
     _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w"); _req(out, torch.bfloat16, "out")
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
@@ -129,7 +135,7 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional
         _req(bias, torch.float32, "bias")
     rc = lib.pi3b_gemm_qkv(_stream(), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, num_heads, K, _ptr(bias),
                            out.data_ptr(), out.stride(0), _ptr(qk_norm), eps, _ptr(cs_table), rows, tokens_per_frame,
-                           n_special, patch_w)
+                           n_special, patch_w, q_scale)
     _lib.check(rc, "pi3b_gemm_qkv")
     return out
 
@@ -235,9 +241,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def qknorm_rope(qkv: torch.Tensor, num_heads: int, tokens_per_frame: int, n_special: int, patch_w: int,
                 cs_table: Optional[torch.Tensor], qn: Optional[tuple] = None, kn: Optional[tuple] = None,
-                eps: float = 1e-5) -> torch.Tensor:
+                eps: float = 1e-5, q_scale: float = 1.0) -> torch.Tensor:
     """In place on the q and k thirds of packed qkv: optional LayerNorm(64) then RoPE-2D (if cs_table given).
-    cs_table: fp32 [max_pos+1, 16, 2] = (cos, sin) of pos * base^(-j/16)."""
+    cs_table: fp32 [max_pos+1, 16, 2] = (cos, sin) of pos * base^(-j/16). q_scale as in `gemm_qkv`."""
     lib = _lib.load()
     _req(qkv, torch.bfloat16, "qkv")
     assert qkv.dim() == 2 and qkv.stride(1) == 1
@@ -252,7 +258,8 @@ def qknorm_rope(qkv: torch.Tensor, num_heads: int, tokens_per_frame: int, n_spec
         assert cs_table.is_contiguous() and cs_table.shape[1:] == (16, 2)
         rows = cs_table.shape[0]
     rc = lib.pi3b_qknorm_rope(_stream(), qkv.data_ptr(), qkv.stride(0), qkv.shape[0], num_heads, tokens_per_frame,
-                              n_special, patch_w, *ptrs, eps, _ptr(cs_table), rows, 1 if cs_table is not None else 0)
+                              n_special, patch_w, *ptrs, eps, _ptr(cs_table), rows, 1 if cs_table is not None else 0,
+                              q_scale)
     _lib.check(rc, "pi3b_qknorm_rope")
     return qkv
 

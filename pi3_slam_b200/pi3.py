@@ -81,6 +81,10 @@ class Pi3(nn.Module):
         # q/k LayerNorm + RoPE fused into the QKV GEMM epilogue (bit-identical to the separate pi3b_qknorm_rope pass, which
         # PI3B_FUSE_QK=0 brings back for A/B runs)
         self.fuse_qk_epilogue: bool = os.environ.get("PI3B_FUSE_QK", "1") != "0"
+        # softmax scale * log2(e) folded into q where q is post-processed anyway (decoder and head-decoder blocks): one
+        # rounding of q * c instead of q, and the chunk-global attention kernel skips the scale-and-subtract per score
+        # (PI3B_PRESCALE_Q=0 for A/B runs and for the parity test that compares both)
+        self.prescale_q: bool = os.environ.get("PI3B_PRESCALE_Q", "1") != "0"
         # when set to a list, (local_done, gather_done) CUDA events of every sequence-parallel layer are appended:
         # their distance is the all-gather time the local attention did not hide
         self.sp_events: Optional[list] = None
@@ -304,7 +308,7 @@ class Pi3(nn.Module):
         return dict(group=group, G=G, rank=r, rows=rows, m_max=m_max, remote_rows=R, copies=copies,
                     all_rows=sum(rows), equal=len(set(rows)) == 1)
 
-    def _sp_global_attention(self, qkv, att, bufs, sp: dict, M: int) -> None:
+    def _sp_global_attention(self, qkv, att, bufs, sp: dict, M: int, scale: float = 0.125) -> None:
         """Chunk-global attention of the M local query rows against the K/V rows of every rank of the group
         (`att` = softmax(q K^T / 8) V over all sum(rows) keys). K|V cross NVLink as one NCCL all-gather per layer."""
         import torch.distributed as dist
@@ -316,11 +320,11 @@ class Pi3(nn.Module):
             if not sp["equal"]:
                 raise ValueError("sp_overlap=False needs the same number of frames on every rank")
             dist.all_gather_into_tensor(kv_all, kv_send, group=sp["group"])
-            ops.attention_q_kv(qkv, kv_all, att, 1, M, sp["all_rows"], HEADS, 0.125)
+            ops.attention_q_kv(qkv, kv_all, att, 1, M, sp["all_rows"], HEADS, scale)
             return
         work = dist.all_gather_into_tensor(kv_all, kv_send, group=sp["group"], async_op=True)   # NCCL's own stream
         lse = bufs["lse"]
-        ops.attention_q_kv_lse(qkv, kv_send[:M], att, lse[0], 1, M, M, HEADS, 0.125)             # local block meanwhile
+        ops.attention_q_kv_lse(qkv, kv_send[:M], att, lse[0], 1, M, M, HEADS, scale)             # local block meanwhile
         if self.sp_events is not None:
             e0 = torch.cuda.Event(enable_timing=True); e0.record()
         work.wait()                                       # the current stream waits for the gathered rows
@@ -330,7 +334,7 @@ class Pi3(nn.Module):
         for dst, src, n in sp["copies"]:
             kv_all[dst:dst + n].copy_(kv_all[src:src + n])
         R = sp["remote_rows"]
-        ops.attention_q_kv_lse(qkv, kv_all[:R], bufs["att_remote"], lse[1], 1, M, R, HEADS, 0.125)
+        ops.attention_q_kv_lse(qkv, kv_all[:R], bufs["att_remote"], lse[1], 1, M, R, HEADS, scale)
         ops.attention_merge([att, bufs["att_remote"]], [lse[0], lse[1]], att, HEADS)
 
     def _block(self, x, b, bufs, num_seqs, seq_len, T, pw, cs, rope: bool, sp=None) -> None:
@@ -339,23 +343,28 @@ class Pi3(nn.Module):
         every rank of the group, all-gathered over NCCL."""
         h, qkv, att, mlp = bufs["h"], bufs["qkv"], bufs["att"], bufs["mlp"]
         ops.layernorm(x, b["n1"][0], b["n1"][1], 1e-6, h)
+        # blocks whose q passes through a post-processing step anyway (q/k norm and / or RoPE) fold the softmax scale
+        # into it: exp2 then applies to the attention accumulator as is (see ops.Q_PRESCALE)
+        prescale = self.prescale_q and (rope or b["qn"] is not None)
+        q_scale, scale = (ops.Q_PRESCALE, ops.ATTN_SCALE_PRESCALED) if prescale else (1.0, 0.125)
         if (rope or b["qn"] is not None) and self.fuse_qk_epilogue:
             # q/k LayerNorm(64) + RoPE-2D inside the QKV GEMM's epilogue (one launch, no extra pass over q and k)
-            ops.gemm_qkv(h, b["qkv_w"], qkv, b["qkv_b"], HEADS, b["qkn"], 1e-5, cs if rope else None, T, N_SPECIAL, pw)
+            ops.gemm_qkv(h, b["qkv_w"], qkv, b["qkv_b"], HEADS, b["qkn"], 1e-5, cs if rope else None, T, N_SPECIAL, pw,
+                         q_scale)
         else:
             ops.gemm(h, b["qkv_w"], qkv, bias=b["qkv_b"])
             if rope or b["qn"] is not None:
-                ops.qknorm_rope(qkv, HEADS, T, N_SPECIAL, pw, cs if rope else None, b["qn"], b["kn"], 1e-5)
+                ops.qknorm_rope(qkv, HEADS, T, N_SPECIAL, pw, cs if rope else None, b["qn"], b["kn"], 1e-5, q_scale)
         if sp is not None:
-            self._sp_global_attention(qkv, att, bufs, sp, seq_len)
+            self._sp_global_attention(qkv, att, bufs, sp, seq_len, scale)
         elif self.global_attn_events is not None and seq_len != T:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.attention_qkv(qkv, att, num_seqs, seq_len, HEADS, 0.125)
+            ops.attention_qkv(qkv, att, num_seqs, seq_len, HEADS, scale)
             e1.record()
             self.global_attn_events.append((e0, e1))
         else:
-            ops.attention_qkv(qkv, att, num_seqs, seq_len, HEADS, 0.125)
+            ops.attention_qkv(qkv, att, num_seqs, seq_len, HEADS, scale)
         ops.gemm(att, b["proj_w"], x, bias=b["proj_b"], gamma=b["ls1"], resid=x)
         ops.layernorm(x, b["n2"][0], b["n2"][1], 1e-6, h)
         ops.gemm(h, b["fc1_w"], mlp, bias=b["fc1_b"], act=ops.ACT_GELU)

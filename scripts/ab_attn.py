@@ -19,6 +19,20 @@ for (B, S, H, it) in [(100, 1004, 16, 10), (1, 64300, 16, 4), (1, 100400, 16, 5)
     qkv = torch.randn(B * S, 3 * H * 64, device='cuda').bfloat16(); out = torch.empty(B * S, H * 64, device='cuda', dtype=torch.bfloat16)
     t = time_cuda(lambda: ops.attention_qkv(qkv, out, B, S, H), iters=it, warmup=2)
     res[f'{B}x{S}'] = (round(t * 1e3, 3), round(4.0 * B * H * S * S * 64 / t / 1e12, 1))
+# queries pre-multiplied by scale * log2(e) (what pi3b_gemm_qkv's q_scale emits), scale = ln 2: the zero-reference softmax
+import math
+C = H * 64
+qs = qkv.clone(); qs[:, :C] = (qs[:, :C].float() * (0.125 * 1.4426950408889634)).bfloat16()
+t = time_cuda(lambda: ops.attention_qkv(qs, out, B, S, H, scale=math.log(2.0)), iters=it, warmup=2)
+res['prescaled_1x100400'] = (round(t * 1e3, 3), round(4.0 * B * H * S * S * 64 / t / 1e12, 1))
+rows = torch.arange(0, S, 997, device='cuda')
+errs = []
+for h in (0, 7, 15):
+    qh = qs[rows, h * 64:(h + 1) * 64].double(); kh = qs[:, C + h * 64:C + (h + 1) * 64].double(); vh = qs[:, 2 * C + h * 64:2 * C + (h + 1) * 64].double()
+    ref = torch.softmax(qh @ kh.t() * math.log(2.0), dim=-1) @ vh
+    errs.append(float((out[rows, h * 64:(h + 1) * 64].double() - ref).norm() / ref.norm()))
+res['prescaled_err'] = float('%%.2e' %% max(errs))
+del qs
 # sequence-parallel shape: 1/8 of the cfg2 queries against all keys
 S, Q, H = 100400, 12550, 16
 q = qkv[:Q]; kv = qkv[:, H * 64:].contiguous(); out = torch.empty(Q, H * 64, device='cuda', dtype=torch.bfloat16)

@@ -158,3 +158,33 @@ def test_bounded_reference_softmax_and_its_fallback(outlier):
     assert err.item() < 1e-2, f"rel err {err.item():.3e}"
     worst = ((out[rows].double() - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
     assert worst < 3e-2, worst
+
+
+@pytest.mark.parametrize("q_gain,what", [(1.0, "zero reference"), (9.0, "bound above 100: fixed / online reference")])
+def test_prescaled_queries_zero_reference_softmax(q_gain, what):
+    """scale = ln 2 announces queries that already carry scale * log2(e) (pi3b_gemm_qkv's q_scale): the long-sequence kernel
+    then exponentiates the accumulator as is when |q| max|k| <= 100, and must fall back to a subtracted reference when the
+    bound is larger (q_gain = 9: |q| max|k| ~ 130). Both against an fp64 softmax on sampled rows."""
+    import math
+    from pi3_slam_b200 import ops
+
+    S, H = 9100, 2
+    C = H * 64
+    torch.manual_seed(11)
+    qkv = torch.randn(S, 3 * C, device="cuda")
+    qkv[:, :C] *= ops.Q_PRESCALE * q_gain
+    qkv = qkv.bfloat16()
+    out = torch.full((S, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attention_qkv(qkv, out, 1, S, H, scale=ops.ATTN_SCALE_PRESCALED)
+    rows = torch.arange(0, S, 13, device="cuda")
+    q, k, v = qkv.double().view(S, 3, H, 64).permute(1, 2, 0, 3)
+    ref = (torch.softmax(q[:, rows] @ k.transpose(-1, -2) * math.log(2.0), dim=-1) @ v).permute(1, 0, 2).reshape(len(rows), C)
+    assert torch.isfinite(out.float()).all()
+    err = (out[rows].double() - ref).norm() / ref.norm()
+    assert err.item() < 1e-2, f"{what}: rel err {err.item():.3e}"
+    # and the log-sum-exp the sequence-parallel merge relies on (log2 domain)
+    lse = torch.empty(H, S, device="cuda", dtype=torch.float32)
+    kv = qkv[:, C:].contiguous()
+    ops.attention_q_kv_lse(qkv, kv, out, lse, 1, S, S, H, scale=ops.ATTN_SCALE_PRESCALED)
+    want = torch.logsumexp(q[:, rows] @ k.transpose(-1, -2) * math.log(2.0), dim=-1) / math.log(2.0)
+    assert (lse[:, rows].double() - want).abs().max().item() < 2e-2

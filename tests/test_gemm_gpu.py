@@ -35,6 +35,12 @@ CASES = [
     (1999, 512, 512, "fp32", True, True, False, True, 2),      # camera res-conv: relu + residual
     (37, 9, 512, "fp32", True, True, False, False, 0),
     (30000, 588, 1024, "fp32", True, True, False, False, 0),
+    # CTA-pair kernels, one case per epilogue instantiation and its fall-backs
+    (19999, 1280, 512, "bf16", True, True, True, False, 0),    # streamlined fp32 epilogue without a residual, 5 column tiles
+    (19999, 1024, 1024, "bf16", True, True, False, True, 2),   # streamlined: ReLU + residual
+    (19999, 1152, 512, "bf16", True, True, True, True, 0),     # N % 256 != 0: general epilogue with a residual
+    (19999, 1024, 512, "bf16", False, True, True, True, 0),    # bf16 output with a residual: general epilogue
+    (19999, 1024, 512, "bf16", True, True, False, False, 1),   # GELU into fp32: general epilogue
 ]
 
 
@@ -68,13 +74,47 @@ def test_gemm_matches_torch(M, N, K, dt, out_f32, has_bias, has_gamma, has_resid
     assert maxabs < 0.05 * max(1.0, ref.abs().max().item())
 
 
+def test_residual_into_a_separate_output_and_row_regrouping():
+    """The streamlined residual epilogue with out != resid, and the row-regrouped residual GEMM (patch embedding:
+    GEMM row m lands on row (m // grp_in) * grp_out + off + m % grp_in) at a size that runs the CTA-pair kernel."""
+    from pi3_slam_b200 import ops
+
+    torch.manual_seed(3)
+    dev = "cuda"
+    M, N, K = 20001, 1024, 512
+    a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias, gamma = torch.randn(N, device=dev), torch.rand(N, device=dev) + 0.5
+    resid = torch.randn(M, N, device=dev)
+    keep = resid.clone()
+    out = torch.full((M, N), float("nan"), device=dev)
+    ops.gemm(a, w, out, bias=bias, gamma=gamma, resid=resid)
+    ref = _ref(a, w, bias, gamma, keep, 0)
+    assert torch.equal(resid, keep)
+    assert ((out - ref).norm() / ref.norm()).item() < 1e-5
+
+    P, T, off = 999, 1004, 5
+    frames = 21
+    a = (torch.randn(frames * P, K, device=dev) * 0.5).bfloat16()
+    x = torch.randn(frames * T, N, device=dev)
+    keep = x.clone()
+    ops.gemm(a, w, x, bias=bias, resid=x, row_remap=(P, T, off))
+    y = (a.float() @ w.float().t() + bias).view(frames, P, N)
+    want = keep.view(frames, T, N).clone()
+    want[:, off:] += y
+    assert torch.equal(x.view(frames, T, N)[:, :off], keep.view(frames, T, N)[:, :off])   # special-token rows untouched
+    assert ((x.view(frames, T, N) - want).norm() / want.norm()).item() < 1e-5
+
+
 # M: narrow-tile path (< 148 wide tiles), wide single-CTA path (PI3B_GEMM_CLUSTER=0 in the subprocess case below) and the
 # default wide 2-CTA-cluster path; ragged M tails; (norm, rope) combinations used by the model: decoder blocks (both),
 # head decoders (rope only).
 @pytest.mark.parametrize("M,T,pw", [(643 * 3, 643, 29), (1004 * 20, 1004, 37), (261 * 5 + 7, 261, 16)])
-@pytest.mark.parametrize("norm,rope", [(True, True), (False, True), (True, False)])
-def test_fused_qkv_epilogue_is_bit_identical_to_gemm_plus_qknorm_rope(M, T, pw, norm, rope):
-    """pi3b_gemm_qkv == pi3b_gemm followed by pi3b_qknorm_rope, bit for bit (shared arithmetic, csrc/qk_math.cuh)."""
+@pytest.mark.parametrize("norm,rope,q_scale", [(True, True, 1.0), (False, True, 1.0), (True, False, 1.0),
+                                               (True, True, 0.125 * 1.4426950408889634), (False, True, 0.18033688)])
+def test_fused_qkv_epilogue_is_bit_identical_to_gemm_plus_qknorm_rope(M, T, pw, norm, rope, q_scale):
+    """pi3b_gemm_qkv == pi3b_gemm followed by pi3b_qknorm_rope, bit for bit (shared arithmetic, csrc/qk_math.cuh), with and
+    without the softmax scale folded into the queries."""
     from pi3_slam_b200 import ops
 
     H, K = 16, 1024
@@ -92,10 +132,19 @@ def test_fused_qkv_epilogue_is_bit_identical_to_gemm_plus_qknorm_rope(M, T, pw, 
 
     want = torch.empty(M, 3 * 64 * H, device="cuda", dtype=torch.bfloat16)
     ops.gemm(a, w, want, bias=bias)
-    ops.qknorm_rope(want, H, T, 5, pw, cs if rope else None, qn if norm else None, kn if norm else None, 1e-5)
+    if q_scale != 1.0:
+        unscaled = want.clone()
+        ops.qknorm_rope(unscaled, H, T, 5, pw, cs if rope else None, qn if norm else None, kn if norm else None, 1e-5)
+    ops.qknorm_rope(want, H, T, 5, pw, cs if rope else None, qn if norm else None, kn if norm else None, 1e-5, q_scale)
     got = torch.full_like(want, float("nan"))
-    ops.gemm_qkv(a, w, got, bias, H, qkn if norm else None, 1e-5, cs if rope else None, T, 5, pw)
+    ops.gemm_qkv(a, w, got, bias, H, qkn if norm else None, 1e-5, cs if rope else None, T, 5, pw, q_scale)
     torch.cuda.synchronize()
+    if q_scale != 1.0:
+        # only the queries are scaled (k and v untouched), by q_scale up to the one bf16 rounding
+        C = 64 * H
+        assert torch.equal(got[:, C:], unscaled[:, C:])
+        rel = (got[:, :C].float() - unscaled[:, :C].float() * q_scale).abs() / (unscaled[:, :C].float().abs() * q_scale + 1e-20)
+        assert rel.max().item() <= 2.0 ** -7      # two bf16 roundings (x, then x * q_scale), half an ulp = 2^-8 relative each
     assert torch.isfinite(got.float()).all()
     neq = (got.view(torch.int16) != want.view(torch.int16)).sum().item()
     assert neq == 0, f"{neq} of {got.numel()} elements differ, max |d| {(got.float() - want.float()).abs().max().item():.3e}"

@@ -152,3 +152,22 @@ def test_fused_qk_epilogue_forward_is_bit_identical_to_separate_pass(model_and_s
         model.fuse_qk_epilogue = True
     for k in fused:
         assert torch.equal(fused[k], plain[k]), k
+
+
+def test_prescaled_queries_forward_stays_within_the_bf16_tolerance(model_and_sd):
+    """Pi3.prescale_q folds the softmax scale into q before its rounding to bf16: a differently placed rounding, so the
+    outputs are not bit-identical to the unscaled schedule — they must agree to the tolerance of the bf16 path itself."""
+    from pi3_slam_b200.synthetic import make_frames
+
+    model, _ = model_and_sd
+    imgs = make_frames(3, 56, 70)[None].cuda()
+    assert model.prescale_q
+    on = {k: v.clone() for k, v in model(imgs).items()}
+    model.prescale_q = False
+    try:
+        off = model(imgs)
+    finally:
+        model.prescale_q = True
+    for k, tol in (("points", 5e-3), ("local_points", 5e-3), ("conf", 1e-2), ("camera_poses", 5e-3)):
+        rel = ((on[k] - off[k]).norm() / off[k].norm()).item()
+        assert rel < tol, f"{k}: {rel:.3e}"
