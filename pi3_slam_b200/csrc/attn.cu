@@ -49,6 +49,9 @@ namespace pi3b {
 #ifndef PI3B_POLY_PAIRS
 #define PI3B_POLY_PAIRS 3
 #endif
+#ifndef PI3B_POLY_PAIRS_ZERO   // the same share for the zero-reference steps of the three-tile kernel
+#define PI3B_POLY_PAIRS_ZERO 4
+#endif
 #ifndef PI3B_POLY_DEG
 #define PI3B_POLY_DEG 2
 #endif
@@ -124,10 +127,16 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
 // two exp2 at once on the FMA pipe: clamp (ALU pipe), round-to-integer via the 1.5*2^23 trick, minimax polynomial of 2^f
 // on [-0.5, 0.5] (degree 2: max rel. error 1.73e-3 = 2^-9.2; degree 3: 7.5e-5), exponent spliced in with one integer
 // shift-add per element. 7 (8) packed/scalar instructions for two elements next to 2 MUFU + nothing for the ex2 path.
+// CLAMP = false: the caller guarantees x >= -126 (zero-reference steps: every score is within [-100, 100]), the two FMNMX
+// per pair are dropped.
+template <bool CLAMP = true>
 __device__ __forceinline__ void poly_exp2_x2(uint64_t x, float& p0, float& p1) {
-  float x0, x1;
-  unpack2(x, x0, x1);
-  const uint64_t xc = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  uint64_t xc = x;
+  if (CLAMP) {
+    float x0, x1;
+    unpack2(x, x0, x1);
+    xc = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  }
   const uint64_t magic = pack2(12582912.0f, 12582912.0f);
   const uint64_t t = fadd2(xc, magic);
   const uint64_t r = fadd2(t, pack2(-12582912.0f, -12582912.0f));
@@ -152,7 +161,7 @@ __device__ __forceinline__ void poly_exp2_x2(uint64_t x, float& p0, float& p1) {
 // exponentials of NCOL scores held in registers: a[c] (fp32 bit patterns) -> packed bf16 P in out[0 .. NCOL/2), row sum
 // accumulated in the packed pair `lsum`. x = score * scale_log2 - m_used.
 // RAW = true: the scores are already in their final units (log2 domain, reference 0): no scale-and-subtract at all.
-template <int NCOL, bool RAW = false>
+template <int NCOL, bool RAW = false, bool CLAMP = true, int PAIRS = PI3B_POLY_PAIRS>
 __device__ __forceinline__ void exp_block(const uint32_t* a, uint32_t* out, uint64_t sc2, uint64_t negm2, uint64_t& lsum) {
 #pragma unroll
   for (int c = 0; c < NCOL; c += 2) {
@@ -160,9 +169,9 @@ __device__ __forceinline__ void exp_block(const uint32_t* a, uint32_t* out, uint
     const uint64_t x = RAW ? xin : ffma2(xin, sc2, negm2);
     float p0, p1;
     // pairs are spread evenly over the row so that ptxas can interleave the FMA-pipe chains with the MUFU stream
-    const bool poly = (((c >> 1) % 8) * PI3B_POLY_PAIRS) % 8 < PI3B_POLY_PAIRS;
+    const bool poly = (((c >> 1) % 8) * PAIRS) % 8 < PAIRS;
     if (poly) {
-      poly_exp2_x2(x, p0, p1);
+      poly_exp2_x2<CLAMP>(x, p0, p1);
     } else {
       float x0, x1;
       unpack2(x, x0, x1);
@@ -545,7 +554,9 @@ attn_fwd_kernel_t3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (MASK) mask_tail<64>(sr, 0, p.kv_len - j * 64);
         // (moving the two polls into the middle of the exponentials measured no gain: profiles/r02_attn_poly_ab.log "mid2")
         const bool pv_ready = mbar_try_wait(&pv_done[t], (j - 1) & 1);
-        exp_block<64, RAW>(sr, sr, sc2, negm2, lsum);
+        // masked columns are -inf: the last step clamps. Without clamp and scale-and-subtract the polynomial costs 7
+        // instructions per pair: the zero-reference steps take half of the pairs (PAIRS_ZERO = 4 of 8) on the FMA pipe
+        exp_block<64, RAW, !(RAW && !MASK), RAW ? PI3B_POLY_PAIRS_ZERO : PI3B_POLY_PAIRS>(sr, sr, sc2, negm2, lsum);
         s_ready = !MASK && mbar_try_wait(&s_full[t], (j + 1) & 1);
         if (!pv_ready) mbar_wait(&pv_done[t], (j - 1) & 1);
         tc_fence_after();
