@@ -6,7 +6,8 @@
 A "step" is one pi3 forward over one synthetic chunk (default workload cfg2 = BASELINE.json configs[1]:
 100 frames at 378x518, bf16 tensor cores). `value` times steps with the chunk already resident in HBM;
 `e2e` times the same steps through the public `Pi3.forward` call from pinned HOST frames to pinned HOST
-results (H2D of the frames and D2H of all four output maps inside the timed region). For N > 1 (launched
+results (H2D of the frames and D2H of all four output maps of EVERY step inside the timed region; like the product's
+own chunk loop, the uploads and downloads run on a copy stream next to the neighbouring steps' compute). For N > 1 (launched
 by torch.distributed.run, one rank per GPU) every rank runs its own chunk — chunks are independent, there is
 no data-path collective — and `value` is total frames over the max-over-ranks device time ("weak" scaling).
 
@@ -506,17 +507,51 @@ def main():
     h2d = host_frames.numel() * host_frames.element_size()
     d2h = sum(v.numel() * v.element_size() for v in host_out.values())
 
-    def e2e_step():
-        o = model(host_frames.to(dev, non_blocking=True))
-        for k, v in o.items():
-            host_out[k].copy_(v, non_blocking=True)
+    # The loop a streaming caller writes (and `OfflineChunkCreator.process_and_save` runs): a copy stream uploads the next
+    # step's frames while the current forward computes, and the results leave through a device staging copy (0.2 ms) whose
+    # download overlaps the next forward. Every step's H2D and D2H happens inside the timed region; the region ends only
+    # after the last step's results have landed in host memory.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_in = [torch.empty_like(dev_frames) for _ in range(2)]
+    staged = {k: torch.empty_like(v) for k, v in out.items()}
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    in_free = [torch.cuda.Event() for _ in range(2)]
+    staged_full, staged_free = torch.cuda.Event(), torch.cuda.Event()
 
-    e2e_step()
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(in_free[i % 2])          # the forward that read this buffer two steps ago is done
+            dev_in[i % 2].copy_(host_frames, non_blocking=True)
+            in_ready[i % 2].record(copy_stream)
+
+    def e2e_run(steps):
+        cur = torch.cuda.current_stream()
+        for ev in in_free:
+            ev.record(cur)
+        staged_free.record(cur)
+        upload(0)
+        for i in range(steps):
+            if i + 1 < steps:
+                upload(i + 1)
+            cur.wait_event(in_ready[i % 2])
+            o = model(dev_in[i % 2])
+            in_free[i % 2].record(cur)
+            cur.wait_event(staged_free)                     # the previous step's download has left the staging buffers
+            for k, v in o.items():
+                staged[k].copy_(v, non_blocking=True)
+            staged_full.record(cur)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(staged_full)
+                for k in staged:
+                    host_out[k].copy_(staged[k], non_blocking=True)
+                staged_free.record(copy_stream)
+        cur.wait_stream(copy_stream)                        # the last download is inside the timed region
+
+    e2e_run(1)
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     s1.record()
     barrier()
     t2 = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
@@ -566,7 +601,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config,
             "e2e": {"value": world * frames / (e2e_ms_step * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step, "outputs_finite": finite},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step, "outputs_finite": finite,
+                    "pipelined": "H2D of step k+1 and D2H of step k-1 overlap the forward of step k (copy stream)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "model_tflops_per_step": fl["total"] / 1e12,
