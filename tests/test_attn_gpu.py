@@ -188,3 +188,20 @@ def test_prescaled_queries_zero_reference_softmax(q_gain, what):
     ops.attention_q_kv_lse(qkv, kv, out, lse, 1, S, S, H, scale=ops.ATTN_SCALE_PRESCALED)
     want = torch.logsumexp(q[:, rows] @ k.transpose(-1, -2) * math.log(2.0), dim=-1) / math.log(2.0)
     assert (lse[:, rows].double() - want).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,S,H", [(3, 261, 4), (1, 4099, 2)])
+def test_attention_output_stays_inside_its_rows(B, S, H):
+    """Ragged last query tiles of both kernels: nothing is written outside the [B*S, H*64] output (canary rows around it)."""
+    from pi3_slam_b200 import ops
+
+    torch.manual_seed(S)
+    qkv = torch.randn(B * S, 3 * H * 64, device="cuda").bfloat16()
+    pad, sentinel = 256, 777.0
+    big = torch.full((B * S + 2 * pad, H * 64), sentinel, device="cuda", dtype=torch.bfloat16)
+    out = big[pad:pad + B * S]
+    ops.attention_qkv(qkv, out, B, S, H)
+    torch.cuda.synchronize()
+    assert bool((big[:pad] == sentinel).all()) and bool((big[pad + B * S:] == sentinel).all())
+    ref = _ref(qkv, B, S, H)
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 1e-2

@@ -148,3 +148,55 @@ def test_fused_qkv_epilogue_is_bit_identical_to_gemm_plus_qknorm_rope(M, T, pw, 
     assert torch.isfinite(got.float()).all()
     neq = (got.view(torch.int16) != want.view(torch.int16)).sum().item()
     assert neq == 0, f"{neq} of {got.numel()} elements differ, max |d| {(got.float() - want.float()).abs().max().item():.3e}"
+
+
+def _guarded(rows, cols, dtype, pad_rows=64):
+    """A [rows, cols] view in the middle of a larger buffer filled with a sentinel: (view, check) — check() asserts that
+    nothing outside the view was written (the epilogues store through transposed staging buffers, 8 rows per instruction:
+    a row-bound slip on a ragged last tile would land here)."""
+    sentinel = 12345.0
+    big = torch.full((rows + 2 * pad_rows, cols), sentinel, device="cuda", dtype=dtype)
+    view = big[pad_rows:pad_rows + rows]
+
+    def check():
+        assert bool((big[:pad_rows] == sentinel).all()) and bool((big[pad_rows + rows:] == sentinel).all())
+    return view, check
+
+
+@pytest.mark.parametrize("M", [19999, 20001, 2088 + 37])
+def test_epilogue_stores_stay_inside_a_ragged_last_tile(M):
+    """Every epilogue instantiation on an M that is not a multiple of 128 (nor of 8), output surrounded by canaries."""
+    from pi3_slam_b200 import ops
+
+    torch.manual_seed(M)
+    K, H = 512, 16
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    bias1 = torch.randn(1024, device="cuda")
+    w1 = (torch.randn(1024, K, device="cuda") * 0.05).bfloat16()
+    # general epilogue, bf16 out (+ GELU)
+    out, check = _guarded(M, 1024, torch.bfloat16)
+    ops.gemm(a, w1, out, bias=bias1, act=ops.ACT_GELU)
+    torch.cuda.synchronize(); check()
+    ref = torch.nn.functional.gelu(a.float() @ w1.float().t() + bias1)
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 5e-3
+    # fp32 residual read-modify-write in place
+    x, check = _guarded(M, 1024, torch.float32)
+    x.copy_(torch.randn(M, 1024, device="cuda"))
+    keep = x.clone()
+    ops.gemm(a, w1, x, bias=bias1, gamma=torch.full((1024,), 0.5, device="cuda"), resid=x)
+    torch.cuda.synchronize(); check()
+    ref = keep + 0.5 * (a.float() @ w1.float().t() + bias1)
+    assert ((x - ref).norm() / ref.norm()).item() < 1e-5
+    # fused QKV epilogue
+    T, pw = 261, 16
+    wq = (torch.randn(3 * 64 * H, K, device="cuda") * 0.05).bfloat16()
+    bq = torch.randn(3 * 64 * H, device="cuda") * 0.1
+    qkn = torch.cat([torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda") * 0.1,
+                     torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda") * 0.1]).contiguous()
+    inv_freq = 1.0 / (100.0 ** (torch.arange(0, 32, 2).float() / 32))
+    ang = torch.einsum("i,j->ij", torch.arange(pw + 2, dtype=torch.float32), inv_freq)
+    cs = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous().cuda()
+    qkv, check = _guarded(M, 3 * 64 * H, torch.bfloat16)
+    ops.gemm_qkv(a, wq, qkv, bq, H, qkn, 1e-5, cs, T, 5, pw, ops.Q_PRESCALE)
+    torch.cuda.synchronize(); check()
+    assert torch.isfinite(qkv.float()).all()
