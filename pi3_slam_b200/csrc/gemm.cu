@@ -39,6 +39,7 @@ struct GemmParams {
   const float* qk_norm;
   const float2* cs_table;
   float qk_eps;
+  int cs_rows;     // rows of cs_table (positions 0 .. cs_rows - 1)
   float q_scale;   // queries (columns [0, qk_cols / 2)) are multiplied by this before the final rounding (1 = none)
   int tokens_per_frame, n_special, patch_w;
 };
@@ -47,7 +48,12 @@ constexpr int kBlockM = 128;
 constexpr int kNumEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kNumEpiWarps * 32;
 
-template <int BLOCK_N, int STAGES, bool TWOSM = false>
+// RoPE table rows the fused QKV epilogue can keep in shared memory (144-byte row stride: the 16-byte reads of eight
+// consecutive positions fall into distinct bank groups); longer tables are read from global memory
+constexpr int kCsSmemRows = 60;
+constexpr int kCsRowBytes = 144;
+
+template <int BLOCK_N, int STAGES, bool TWOSM = false, bool QKEPI = false>
 struct GemmSmem {
   static constexpr int A_BYTES = kBlockM * 128;
   static constexpr int B_BYTES = (TWOSM ? BLOCK_N / 2 : BLOCK_N) * 128;   // 2-SM: each CTA of the pair holds half of B
@@ -59,11 +65,15 @@ struct GemmSmem {
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
   // per-epilogue-warp copy of the bias / gamma slice of the current tile (fetched while the main loop runs)
   static constexpr int BG_OFFSET = STG_OFFSET + kNumEpiWarps * STG_BYTES_PER_WARP;
-  static constexpr int BG_BYTES_PER_WARP = 2 * (BLOCK_N / 2) * 4;
+  // (the fused QKV epilogue has no gamma: its half holds the RoPE table instead)
+  static constexpr int BG_BYTES_PER_WARP = (QKEPI ? 1 : 2) * (BLOCK_N / 2) * 4;
   // q/k LayerNorm parameters of the fused QKV epilogue: [q w | q b | k w | k b] x 64 fp32
   static constexpr int QK_OFFSET = BG_OFFSET + kNumEpiWarps * BG_BYTES_PER_WARP;
-  static constexpr int BAR_OFFSET = QK_OFFSET + 4 * 64 * 4;
+  // the (cos, sin) table of the fused QKV epilogue: a row is 16 frequencies x 2 fp32 = 128 bytes, padded to 144
+  static constexpr int CS_OFFSET = QK_OFFSET + 4 * 64 * 4;
+  static constexpr int BAR_OFFSET = CS_OFFSET + (QKEPI ? kCsSmemRows * kCsRowBytes : 0);
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024: manual alignment slack
+  static_assert(TOTAL <= 227 * 1024, "shared-memory budget of one CTA");
 };
 
 // Exact (erf) GELU of nn.GELU() (mlp.py:29), 0.5 x (1 + erf(x / sqrt 2)), with erf from Abramowitz-Stegun 7.1.26
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr bool QK = EPI == 1, FAST = EPI == 2;
   static_assert(!TWOSM || (CL == 2 && !TF32), "the CTA-pair kernel is the bf16 2-CTA-cluster variant");
-  using S = GemmSmem<BLOCK_N, STAGES, TWOSM>;
+  using S = GemmSmem<BLOCK_N, STAGES, TWOSM, EPI == 1>;
   constexpr int ELEM = TF32 ? 4 : 2;
   constexpr int BLOCK_K = 128 / ELEM;  // elements per 128-byte smem row
   constexpr int UMMA_K = 32 / ELEM;    // 16 (bf16) / 8 (tf32): 32 bytes of K per instruction
@@ -239,6 +249,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (QK && (p.qk_mode & 1) && threadIdx.x < 256)
     reinterpret_cast<float*>(smem + S::QK_OFFSET)[threadIdx.x] = __ldg(p.qk_norm + threadIdx.x);
+  // the RoPE table into shared memory: every head of every row needs 2 x 128 bytes of it, and read through the L1/L2 path
+  // right before use those loads were the epilogue warps' largest stall (long scoreboard 17 % of the kernel's samples)
+  if (QK && (p.qk_mode & 2) && p.cs_rows <= kCsSmemRows) {
+    for (int i = threadIdx.x; i < p.cs_rows * 8; i += kGemmThreads) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.cs_table) + i);
+      *reinterpret_cast<float4*>(smem + S::CS_OFFSET + (i >> 3) * kCsRowBytes + (i & 7) * 16) = c4;
+    }
+  }
   tc_fence_before();
   if (CL == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything remote touches them
   else __syncthreads();
@@ -344,7 +362,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (p.gamma) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + mycol));
         }
         *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
-        *reinterpret_cast<float4*>(gamma_s + lane * 4) = g4;
+        if (!QK) *reinterpret_cast<float4*>(gamma_s + lane * 4) = g4;   // (no gamma half in the fused QKV layout)
       }
       __syncwarp();
       // The accumulator buffer goes back to the MMA warp as soon as this warp has its last TMEM read in registers (not
@@ -451,6 +469,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int pos_y = 0, pos_x = 0;
         if (p.qk_mode & 2) qk_row_position(m_in, p.tokens_per_frame, p.n_special, p.patch_w, pos_y, pos_x);
         const uint32_t qk_saddr = smem_u32(smem + S::QK_OFFSET);
+        const uint32_t cs_saddr = p.cs_rows <= kCsSmemRows ? smem_u32(smem + S::CS_OFFSET) : 0u;
         const uint32_t bias_saddr = smem_u32(bias_s);
 #pragma unroll 1
         for (int hd = 0; hd < COLS_PER_WARP / 64; ++hd) {
@@ -476,7 +495,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (n0 < p.qk_cols) {
             const uint32_t norm_saddr = (p.qk_mode & 1) ? qk_saddr + (n0 >= (p.qk_cols >> 1) ? 512u : 0u) : 0u;
-            qk_head_inplace(v, norm_saddr, p.qk_eps, (p.qk_mode & 2) ? p.cs_table : nullptr, pos_y, pos_x);
+            qk_head_inplace(v, norm_saddr, p.qk_eps, (p.qk_mode & 2) ? p.cs_table : nullptr, pos_y, pos_x, cs_saddr);
             if (p.q_scale != 1.0f && n0 < (p.qk_cols >> 1)) {
 #pragma unroll
               for (int j = 0; j < 64; ++j) v[j] = qk_scale_out(v[j], p.q_scale);
@@ -586,7 +605,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 template <int BLOCK_N, int STAGES, bool TF32, int CL, int EPI = 0, bool TWOSM = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
                        cudaStream_t stream) {
-  using S = GemmSmem<BLOCK_N, STAGES, TWOSM>;
+  using S = GemmSmem<BLOCK_N, STAGES, TWOSM, EPI == 1>;
   auto kern = gemm_kernel<BLOCK_N, STAGES, TF32, CL, EPI, TWOSM>;
   static DeviceOnce configured;   // one per template instantiation; the attribute is per device
   const int dev = current_device();
@@ -719,6 +738,7 @@ extern "C" int pi3b_gemm_qkv(void* stream, const void* A, int64_t lda, const voi
   p.qk_norm = qk_norm;
   p.cs_table = reinterpret_cast<const float2*>(cs_table);
   p.qk_eps = eps;
+  p.cs_rows = table_rows;
   p.q_scale = q_scale;
   p.tokens_per_frame = tokens_per_frame > 0 ? tokens_per_frame : 1;
   p.n_special = n_special;

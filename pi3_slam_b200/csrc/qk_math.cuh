@@ -67,9 +67,10 @@ __device__ __forceinline__ void qk_round_bf16_x2(float& a, float& b) {
 
 // One whole head held by one thread: v[64] (fp32 values that are exact bf16 numbers) -> LayerNorm (if norm_saddr != 0: the
 // shared-memory address of 64 weights followed by 64 biases) -> RoPE with positions (pos_y, pos_x) (if cs != nullptr;
-// cs = fp32 [pos][16] (cos, sin)). Results are left in v (unrounded after RoPE: the caller packs to bf16).
+// cs = fp32 [pos][16] (cos, sin); cs_saddr != 0: the same table in shared memory, rows cs_row_bytes apart). Results are
+// left in v (unrounded after RoPE: the caller packs to bf16).
 __device__ __forceinline__ void qk_head_inplace(float* v, uint32_t norm_saddr, float eps, const float2* cs, int pos_y,
-                                                int pos_x) {
+                                                int pos_x, uint32_t cs_saddr = 0, uint32_t cs_row_bytes = 144) {
   if (norm_saddr != 0) {
     float part[8];
 #pragma unroll
@@ -99,7 +100,8 @@ __device__ __forceinline__ void qk_head_inplace(float* v, uint32_t norm_saddr, f
         const float4* t = reinterpret_cast<const float4*>(cs + size_t(pos) * 16);
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float4 c = __ldg(t + (j >> 1));   // (cos, sin) of frequencies j and j + 1
+          // (cos, sin) of frequencies j and j + 1
+          const float4 c = cs_saddr ? qk_lds128(cs_saddr + uint32_t(pos) * cs_row_bytes + (j >> 1) * 16) : __ldg(t + (j >> 1));
           const float a0 = v[32 * h + j], b0 = v[32 * h + j + 16];
           const float a1 = v[32 * h + j + 1], b1 = v[32 * h + j + 17];
           v[32 * h + j] = qk_rope_first(a0, b0, c.x, c.y);
