@@ -124,3 +124,15 @@ def nccl_high_priority_options():
         return opts
     except Exception:
         return None
+
+
+def group_all_ok(ok: bool, group=None, device="cpu") -> bool:
+    """True iff every rank of `group` reports `ok` (one MIN all-reduce of a flag). A chunk that is processed by several
+    ranks (sequence-parallel waves) is entered by all of them or by none: a rank whose frames failed to load must not leave
+    the others waiting in the K/V all-gather — the group skips the chunk together, the reference's degrade-and-continue
+    contract (`offline_chunk_creator.py:299-303`: a failed chunk is reported and skipped)."""
+    import torch
+    import torch.distributed as dist
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())

@@ -25,7 +25,7 @@ import torch
 from . import _lib, ops
 from .host.camera_estimation import (camera_parameters_from_focal_shift, camera_parameters_from_samples,
                                      sample_for_intrinsics, solve_focal_shift_on_device)
-from .host.datasets import ChunkImageDataset, nccl_high_priority_options, plan_waves, split_frames
+from .host.datasets import ChunkImageDataset, group_all_ok, nccl_high_priority_options, plan_waves, split_frames
 from .host.image_utils import calculate_target_size, load_images_u8, resize_u8_on_host
 from .host.keypoints import create_keypoint_extractor
 from .pi3 import Pi3
@@ -483,10 +483,23 @@ class OfflineChunkCreator:
         dev = self.config.device
         for pos, (chunk_idx, ranks) in enumerate(mine):
             _t = time.time()
-            frames_host = pending.popleft().result()
+            load_error = None
+            try:
+                frames_host = pending.popleft().result()
+            except Exception as e:             # unreadable frame(s): report and skip the chunk, like the reference
+                frames_host, load_error = None, e
             t_wait += time.time() - _t
             if pos + depth < len(mine):
                 pending.append(pool.submit(fetch, mine[pos + depth]))
+            if len(ranks) > 1:
+                # a chunk shared by several ranks is entered by all of them or by none (nobody is left in the all-gather)
+                if not group_all_ok(load_error is None, groups[ranks], self.config.device):
+                    print(f"❌ Chunk {chunk_idx + 1}: frames could not be loaded on every rank of {ranks}"
+                          + (f" ({load_error})" if load_error is not None else "") + " — skipped")
+                    continue
+            elif load_error is not None:
+                print(f"❌ Chunk {chunk_idx + 1}: frames could not be loaded ({load_error}) — skipped")
+                continue
             start_idx, end_idx = dataset.chunk_indices[chunk_idx]
             # default_collate turns the nested path list into 1-tuples (reference Appendix B)
             chunk_paths = [(p,) for p in dataset.image_paths[start_idx:end_idx]]

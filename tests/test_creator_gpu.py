@@ -283,6 +283,25 @@ def test_process_and_save_contract(model, tmp_path):
         assert torch.equal(first[k], again[k]), k
 
 
+def test_chunk_with_unreadable_frames_is_reported_and_skipped(model, tmp_path):
+    """A chunk whose frames cannot be loaded is skipped (reference: the chunk loop reports the error and continues); the
+    other chunks and the manifest are unaffected."""
+    from pi3_slam_b200.synthetic import make_frames
+    creator = _creator(model, tmp_path, chunk_length=4, overlap=1, max_num_keypoints=25, keypoint_seed=11)
+    paths = [f"/data/seq/frame_{i:04d}.png" for i in range(9)]
+    index = {p: i for i, p in enumerate(paths)}
+
+    def loader(ps, ts):
+        if paths[5] in ps:                       # frame 5 lives in chunk 1 only (frames 3..6)
+            raise OSError("cannot identify image file")
+        return torch.cat([make_frames(1, *ts, start_index=index[p]) for p in ps])
+
+    files = creator.process_and_save(paths, loader=loader, target_size=(56, 84))
+    assert [os.path.basename(f) for f in files] == ["chunk_000000.pt", "chunk_000002.pt"]
+    manifest = json.load(open(tmp_path / "chunks_manifest.json"))
+    assert [m["chunk_index"] for m in manifest] == [0, 2]
+
+
 def test_umeyama_kernel_and_chunk_alignment():
     from oracle import chunk_oracle as co
     from pi3_slam_b200 import ops

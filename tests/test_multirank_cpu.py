@@ -29,8 +29,11 @@ def _worker(rank, world, port, out_dir):
     full = torch.empty(4, 3)
     dist.all_gather_into_tensor(full, part, group=group)       # frame-ordered gather of per-frame outputs
     assert full[:2].eq(0).all() and full[2:].eq(1).all()
+    # a chunk shared by a group is entered by all of its ranks or by none
+    from pi3_slam_b200.host.datasets import group_all_ok
+    agree = [group_all_ok(True, group), group_all_ok(rank != 1, group), group_all_ok(False, group)]
     with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:
-        json.dump({"mine": mine, "merged": merged}, f)
+        json.dump({"mine": mine, "merged": merged, "agree": agree}, f)
     dist.destroy_process_group()
 
 
@@ -43,6 +46,7 @@ def test_chunk_sharding_and_manifest_gather_world2(tmp_path):
     assert r0["merged"] == r1["merged"]
     assert [e["chunk_index"] for e in r0["merged"]] == list(range(13))
     assert r0["merged"][12]["start_idx"] == 960 and r0["merged"][12]["num_frames"] == 40
+    assert r0["agree"] == [True, False, False] and r1["agree"] == [True, False, False]
 
 
 def test_plan_waves_properties():
