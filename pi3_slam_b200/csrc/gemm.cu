@@ -6,10 +6,12 @@
 // (pi3/models/dinov2/layers/patch_embed.py:65,75).
 //
 // Design: persistent CTAs (one per SM), tile 128 x BLOCK_N x 128 B of K, TMA (SWIZZLE_128B) into a
-// multi-stage smem ring, one elected thread issues tcgen05.mma (cta_group::1, M=128, N=BLOCK_N) into a
-// double-buffered TMEM accumulator, eight epilogue warps drain TMEM with tcgen05.ld (one output row per
-// thread) and apply the fused epilogue  out = [resid +] gamma * act(acc + bias)  straight to HBM, so
-// the epilogue of tile i overlaps the main loop of tile i+1.  Operands: bf16 (kind::f16) or fp32 read
+// multi-stage smem ring, one elected thread issues tcgen05.mma into a double-buffered TMEM accumulator
+// (bf16 wide shapes: CTA pairs, cta_group::2, 256 x 256 per pair; otherwise cta_group::1, M=128, N=BLOCK_N),
+// eight epilogue warps drain TMEM with tcgen05.ld (one output row per thread) and apply the fused epilogue
+// out = [resid +] gamma * act(acc + bias), so the epilogue of tile i overlaps the main loop of tile i+1.
+// The epilogue kind is a template parameter (EPI, see gemm_kernel); every global store writes whole 32-byte
+// sectors (rows are transposed through a per-warp staging buffer). Operands: bf16 (kind::f16) or fp32 read
 // as TF32 (kind::tf32, used for the fp32 heads the reference runs with autocast disabled).
 #include <stdlib.h>
 
