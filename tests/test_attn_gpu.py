@@ -163,7 +163,7 @@ def test_bounded_reference_softmax_and_its_fallback(outlier):
 @pytest.mark.parametrize("q_gain,what", [(1.0, "zero reference"), (9.0, "bound above 100: fixed / online reference")])
 def test_prescaled_queries_zero_reference_softmax(q_gain, what):
     """scale = ln 2 announces queries that already carry scale * log2(e) (pi3b_gemm_qkv's q_scale): the long-sequence kernel
-    then exponentiates the accumulator as is when |q| max|k| <= 100, and must fall back to a subtracted reference when the
+    then exponentiates the accumulator as is when |q| max|k| <= 80, and must fall back to a subtracted reference when the
     bound is larger (q_gain = 9: |q| max|k| ~ 130). Both against an fp64 softmax on sampled rows."""
     import math
     from pi3_slam_b200 import ops
