@@ -44,6 +44,10 @@ def test_version_and_error_string_without_gpu():
     # argument validation happens before any CUDA call, so it works on a CPU-only box
     rc = lib.pi3b_gemm(None, 0, None, 0, None, 0, 1, 1, 1, None, None, None, 0, None, 0, 0, 0, 0, 0, 0)
     assert rc == -1 and b"null pointer" in lib.pi3b_last_error()
+    # the query pre-scale of the fused QKV epilogue must be positive (1 = none)
+    fake = ctypes.c_void_p(0x1000)
+    rc = lib.pi3b_gemm_qkv(None, fake, 1024, fake, 1024, 128, 16, 1024, None, fake, 3072, fake, 1e-5, None, 0, 1, 0, 1, 0.0)
+    assert rc == -1 and b"q_scale" in lib.pi3b_last_error()
 
 
 def test_kernels_are_blackwell_native():
@@ -52,6 +56,9 @@ def test_kernels_are_blackwell_native():
     sass = subprocess.run(["cuobjdump", "-sass", str(LIB_PATH)], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass and "UTMALDG" in sass and "STTM" in sass
     assert "HMMA.16816" not in sass      # no legacy mma.sync tensor path
+    # CTA pairs (tcgen05.mma.cta_group::2 with 2-CTA TMA loads and multicast commits) and packed fp32x2 arithmetic
+    assert "UTCHMMA.2CTA" in sass and "UTMALDG.2D.2CTA" in sass and "UTCBAR.2CTA.MULTICAST" in sass
+    assert "FFMA2" in sass and "FADD2" in sass
     arch = subprocess.run(["cuobjdump", "-lelf", str(LIB_PATH)], capture_output=True, text=True).stdout
     assert "sm_100a" in arch
 
